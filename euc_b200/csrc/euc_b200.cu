@@ -1,0 +1,530 @@
+// euc_b200.cu — C ABI (include/euc_b200.h) over the sm_100a kernels in kernels.cuh.
+// There is no CPU fallback: every entry point that does work launches CUDA kernels on the context's stream.
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared -Xcompiler -fPIC
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace eucb;
+
+namespace {
+
+struct Buf {
+    void* d = nullptr;
+    uint32_t w = 0, h = 0, layers = 0, texel = 0;
+    size_t bytes = 0;
+};
+struct Geom {
+    uint8_t* verts = nullptr;
+    uint32_t stride = 0, n_verts = 0;
+    uint32_t* idx = nullptr;
+    uint32_t n_idx = 0;
+};
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct euc_ctx {
+    int dev = 0;
+    cudaStream_t own = nullptr, stream = nullptr;
+    std::string err;
+    uint64_t next_handle = 1;
+    std::unordered_map<uint64_t, Buf> bufs;
+    std::unordered_map<uint64_t, Geom> geoms;
+    Scratch recs, bbox, tile_count, tile_range, tile_list, draws, uniforms, tmp_verts, tmp_idx;
+    unsigned long long* counters = nullptr;      // device, 4 words
+    unsigned long long* counters_host = nullptr;  // pinned
+    bool stats = false;
+    euc_render_stats last{};
+    int sm_count = 148;
+};
+
+namespace {
+
+int fail(euc_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+#define CU(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e_ = (call);                                                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? EUC_E_OOM : EUC_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(euc_ctx* ctx, Scratch& s, size_t bytes, bool zero_new = false) {
+    if (bytes <= s.cap) return EUC_OK;
+    size_t cap = bytes + bytes / 4 + 4096;
+    if (s.p) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(s.p));
+        s.p = nullptr;
+        s.cap = 0;
+    }
+    CU(cudaMalloc(&s.p, cap));
+    s.cap = cap;
+    if (zero_new) CU(cudaMemsetAsync(s.p, 0, cap, ctx->stream));
+    return EUC_OK;
+}
+
+template <class P> struct PipeInfo {
+    static constexpr bool needs_sampler = false;
+    static constexpr int sampler_format = -1;
+    static constexpr bool vec4_loads = true;
+};
+template <> struct PipeInfo<PipeTeapotShadow> { static constexpr bool needs_sampler = false; static constexpr int sampler_format = -1; static constexpr bool vec4_loads = false; };
+template <> struct PipeInfo<PipeTeapotPhong> { static constexpr bool needs_sampler = true; static constexpr int sampler_format = EUC_TEXEL_F32; static constexpr bool vec4_loads = false; };
+template <> struct PipeInfo<PipeTexCube> { static constexpr bool needs_sampler = true; static constexpr int sampler_format = EUC_TEXEL_RGBA8_TO_F32; static constexpr bool vec4_loads = true; };
+
+struct RenderCall {
+    const euc_pipeline_desc* desc;
+    const Geom* geom;
+    const euc_batch_draw* draws;
+    uint32_t n_draws;
+    const void* uniforms;  // host: n_draws blocks (batch) or one block
+    bool batch;
+    euc_buf pixel, depth;
+    uint32_t row_begin, row_end;
+};
+
+template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
+    using L = RecLayout<P>;
+    using PI = PipeInfo<P>;
+    const euc_pipeline_desc& d = *rc.desc;
+    if (rc.geom->stride < P::VERTEX_BYTES || (rc.geom->stride & 3u)) return fail(ctx, EUC_E_INVALID, "vertex stride %u too small / unaligned for pipeline %d", rc.geom->stride, d.pipeline_id);
+    if (PI::vec4_loads && (rc.geom->stride & 15u)) return fail(ctx, EUC_E_INVALID, "vertex stride must be a multiple of 16 for pipeline %d", d.pipeline_id);
+    if (!std::is_same<P, PipeBlendTris>::value && d.uniform_bytes < sizeof(typename P::Uniforms)) return fail(ctx, EUC_E_INVALID, "uniform block too small (%u < %zu)", d.uniform_bytes, sizeof(typename P::Uniforms));
+    if (PI::needs_sampler && prm.pixel_write) {
+        if (!prm.samp[0].data) return fail(ctx, EUC_E_INVALID, "pipeline %d needs sampler 0", d.pipeline_id);
+        if (prm.samp[0].format != PI::sampler_format) return fail(ctx, EUC_E_INVALID, "sampler 0 has the wrong texel format for pipeline %d", d.pipeline_id);
+    }
+    int rcode;
+    if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * L::BYTES)) != EUC_OK) return rcode;
+    prm.recs = (uint32_t*)ctx->recs.p;
+
+    CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
+    setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm);
+    alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles);
+    CU(cudaGetLastError());
+    // The pair count sizes the list; it is also where out-of-range indices are reported (reference: slice panic).
+    CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long pairs = ctx->counters_host[0];
+    if (ctx->counters_host[3] & 1ull) {
+        // tile_count was incremented by the setup pass: restore the all-zero invariant before bailing out
+        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
+        return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
+    }
+    ctx->last.primitives = prm.n_tris;
+    ctx->last.binned_pairs = pairs;
+    ctx->last.fragments = 0;
+    if (pairs == 0) return EUC_OK;
+    if (pairs > 0xfffffff0ull) return fail(ctx, EUC_E_UNSUPPORTED, "too many (tile, primitive) pairs: %llu", pairs);
+    if ((rcode = ensure(ctx, ctx->tile_list, (size_t)pairs * 4)) != EUC_OK) return rcode;
+    prm.tile_list = (uint32_t*)ctx->tile_list.p;
+    prm.list_capacity = (uint32_t)(ctx->tile_list.cap / 4);
+
+    fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm);
+    sort_lists_kernel<<<(n_tiles + 3) / 4, 128, 0, ctx->stream>>>(prm, n_tiles);
+    const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
+    if (prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write)
+        raster_kernel<P, true><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+    else
+        raster_kernel<P, false><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+    CU(cudaGetLastError());
+    return EUC_OK;
+}
+
+int render_common(euc_ctx* ctx, const RenderCall& rc) {
+    if (!rc.desc || !rc.geom) return fail(ctx, EUC_E_INVALID, "null desc/geom");
+    const euc_pipeline_desc& d = *rc.desc;
+    if (d.pipeline_id < 0 || d.pipeline_id >= EUC_PIPE_COUNT) return fail(ctx, EUC_E_INVALID, "unknown pipeline_id %d", d.pipeline_id);
+    if (d.primitive_kind != EUC_PRIM_TRIANGLE_LIST) return fail(ctx, EUC_E_UNSUPPORTED, "primitive kind %d is not implemented on the device yet (TriangleList only)", d.primitive_kind);
+    if (d.cull_mode < 0 || d.cull_mode > 2 || d.depth_test < 0 || d.depth_test > 3) return fail(ctx, EUC_E_INVALID, "bad cull/depth mode");
+
+    const bool shadow = d.pipeline_id == EUC_PIPE_TEAPOT_SHADOW;
+    const bool pixel_write = d.pixel_write != 0;
+    const bool uses_depth = d.depth_test != EUC_DEPTH_NONE || d.depth_write != 0;
+    // pipeline.rs:256-270
+    if (!pixel_write && !uses_depth) return EUC_OK;
+    const Buf* pb = nullptr;
+    const Buf* db = nullptr;
+    if (rc.pixel) {
+        auto it = ctx->bufs.find(rc.pixel);
+        if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown pixel buffer handle");
+        pb = &it->second;
+    }
+    if (rc.depth) {
+        auto it = ctx->bufs.find(rc.depth);
+        if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown depth buffer handle");
+        db = &it->second;
+    }
+    uint32_t w = 0, h = 0, layers = 1;
+    auto size_of = [](const Buf* b, uint32_t& bw, uint32_t& bh, uint32_t& bl) { bw = b ? b->w : 0; bh = b ? b->h : 0; bl = b ? b->layers : 1; };
+    if (pixel_write && uses_depth) {
+        uint32_t pw, ph, pl, dw, dh, dl;
+        size_of(pb, pw, ph, pl);
+        size_of(db, dw, dh, dl);
+        if (pw != dw || ph != dh || (pb && db && pl != dl))
+            return fail(ctx, EUC_E_SIZE_MISMATCH, "Pixel target size is compatible with depth target size: [%u, %u] vs [%u, %u]", pw, ph, dw, dh);
+        w = pw; h = ph; layers = pb ? pl : dl;
+    } else if (pixel_write) {
+        size_of(pb, w, h, layers);
+    } else {
+        size_of(db, w, h, layers);
+    }
+    if (w == 0 || h == 0) return EUC_OK;  // Empty target: size [0,0] -> needed_threads == 0 -> nothing happens
+    const uint32_t msaa = (uint32_t)std::min(std::max(d.msaa_level, 0), 6);  // pipeline.rs:291-294
+    // pipeline.rs:329-330.  width > 20000*2^msaa makes group_rows 0 and the reference divides by zero.
+    const uint64_t group_rows64 = 20000ull * (1ull << msaa) / std::max<uint64_t>(w, 1);
+    if (group_rows64 == 0) return fail(ctx, EUC_E_UNSUPPORTED, "target width %u > 20000*2^msaa: the reference panics (division by zero, pipeline.rs:330)", w);
+    if (w > 65535u || h > 65535u) return fail(ctx, EUC_E_UNSUPPORTED, "target larger than 65535 in a dimension");
+    const uint32_t group_rows = (uint32_t)std::min<uint64_t>(group_rows64, 0x7fffffffull);
+    if (h / group_rows == 0) return EUC_OK;  // needed_threads == 0: the reference renders nothing (pipeline.rs:330,337)
+
+    uint32_t row_begin = rc.row_begin, row_end = std::min(rc.row_end, h);
+    if (row_begin % TILE) return fail(ctx, EUC_E_INVALID, "row_begin must be a multiple of %d", TILE);
+    if (row_begin >= row_end) return EUC_OK;
+
+    // draws
+    std::vector<DrawDev> dd(rc.n_draws);
+    uint64_t tri_total = 0;
+    const uint32_t stream_len = rc.geom->idx ? rc.geom->n_idx : rc.geom->n_verts;
+    for (uint32_t i = 0; i < rc.n_draws; ++i) {
+        const euc_batch_draw& b = rc.draws[i];
+        if ((uint64_t)b.first + b.count > stream_len) return fail(ctx, EUC_E_OUT_OF_BOUNDS, "draw %u reads past the end of the vertex stream", i);
+        if (b.layer >= layers) return fail(ctx, EUC_E_INVALID, "draw %u targets layer %u of %u", i, b.layer, layers);
+        dd[i] = DrawDev{b.first, b.count, b.base_vertex, b.layer, (uint32_t)tri_total, b.count / 3};  // trailing partial primitive dropped (pipeline.rs:283)
+        tri_total += b.count / 3;
+    }
+    if (tri_total == 0) return EUC_OK;
+    if (tri_total > 0x7fffffffull) return fail(ctx, EUC_E_UNSUPPORTED, "too many primitives");
+
+    Params prm{};
+    prm.w = w; prm.h = h; prm.layers = layers;
+    prm.tiles_x = (w + TILE - 1) / TILE; prm.tiles_y = (h + TILE - 1) / TILE;
+    prm.row_begin = row_begin; prm.row_end = row_end;
+    prm.group_rows = group_rows; prm.msaa_level = msaa;
+    prm.pixel = pb ? (uint32_t*)pb->d : nullptr;
+    prm.depth = db ? (float*)db->d : nullptr;
+    prm.depth_test = d.depth_test; prm.depth_write = d.depth_write != 0; prm.pixel_write = pixel_write && !shadow; prm.uses_depth = uses_depth;
+    if (prm.pixel_write && !prm.pixel) return EUC_OK;
+    if (uses_depth && !prm.depth) {
+        // Empty depth target reads 0.0 and drops writes (texture.rs:312-317); size [0,0] only reaches here when
+        // pixel_write is false, which returned above.  With both targets, sizes would have mismatched.
+        return EUC_OK;
+    }
+    prm.zclip = d.z_clip_enabled != 0; prm.zmin = d.z_clip_min; prm.zmax = d.z_clip_max;
+    prm.cull = d.cull_mode; prm.flip_y = d.y_axis_up ? -1.0f : 1.0f;
+    prm.vertices = rc.geom->verts; prm.vstride = rc.geom->stride; prm.n_vertices = rc.geom->n_verts;
+    prm.indices = rc.geom->idx;
+    prm.n_draws = rc.n_draws; prm.n_tris = (uint32_t)tri_total;
+    prm.stats = ctx->stats ? 1 : 0;
+    prm.counters = ctx->counters;
+
+    for (int i = 0; i < EUC_MAX_SAMPLERS; ++i) {
+        const euc_sampler_desc& s = d.samplers[i];
+        prm.samp[i] = SamplerDev{nullptr, 0, 0, s.format, s.filter, s.wrap};
+        if (s.buf) {
+            auto it = ctx->bufs.find(s.buf);
+            if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "sampler %d: unknown buffer handle", i);
+            if (it->second.w == 0 || it->second.h == 0) return fail(ctx, EUC_E_INVALID, "sampler %d: empty texture (texture.rs:63-66)", i);
+            if (s.filter < 0 || s.filter > 1 || s.wrap < 0 || s.wrap > 3 || s.format < 0 || s.format > 1) return fail(ctx, EUC_E_INVALID, "sampler %d: bad filter/wrap/format", i);
+            prm.samp[i].data = it->second.d;
+            prm.samp[i].w = it->second.w;
+            prm.samp[i].h = it->second.h;
+        }
+    }
+
+    int rcode;
+    if ((rcode = ensure(ctx, ctx->draws, dd.size() * sizeof(DrawDev))) != EUC_OK) return rcode;
+    CU(cudaMemcpyAsync(ctx->draws.p, dd.data(), dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
+    prm.draws = (const DrawDev*)ctx->draws.p;
+    if (rc.batch) {
+        if (d.uniform_bytes == 0 || !rc.uniforms) {
+            prm.uniforms = nullptr;
+        } else {
+            const size_t ub = (size_t)d.uniform_bytes * rc.n_draws;
+            if ((d.uniform_bytes & 15u)) return fail(ctx, EUC_E_INVALID, "batch uniform blocks must be a multiple of 16 bytes");
+            if ((rcode = ensure(ctx, ctx->uniforms, ub)) != EUC_OK) return rcode;
+            CU(cudaMemcpyAsync(ctx->uniforms.p, rc.uniforms, ub, cudaMemcpyHostToDevice, ctx->stream));
+            prm.uniforms = (const uint8_t*)ctx->uniforms.p;
+            prm.uniform_stride = d.uniform_bytes;
+        }
+    } else {
+        if (d.uniform_bytes > sizeof(prm.uni_inline)) return fail(ctx, EUC_E_INVALID, "uniform block larger than %zu bytes", sizeof(prm.uni_inline));
+        if (d.uniform_bytes && !rc.uniforms) return fail(ctx, EUC_E_INVALID, "uniform_bytes > 0 but uniforms is NULL");
+        if (d.uniform_bytes) std::memcpy(prm.uni_inline, rc.uniforms, d.uniform_bytes);
+        prm.uniforms = nullptr;
+    }
+    // the staged copies above read pageable host memory synchronously w.r.t. the caller; dd lives until return.
+    const uint32_t n_tiles = prm.tiles_x * prm.tiles_y * layers;
+    if ((rcode = ensure(ctx, ctx->bbox, (size_t)prm.n_tris * sizeof(uint2))) != EUC_OK) return rcode;
+    if ((rcode = ensure(ctx, ctx->tile_count, (size_t)n_tiles * 4, true)) != EUC_OK) return rcode;
+    if ((rcode = ensure(ctx, ctx->tile_range, (size_t)n_tiles * sizeof(uint2))) != EUC_OK) return rcode;
+    prm.tri_bbox = (uint2*)ctx->bbox.p;
+    prm.tile_count = (uint32_t*)ctx->tile_count.p;
+    prm.tile_range = (uint2*)ctx->tile_range.p;
+
+    switch (d.pipeline_id) {
+        case EUC_PIPE_TEAPOT_SHADOW: rcode = render_typed<PipeTeapotShadow>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_TEAPOT_PHONG: rcode = render_typed<PipeTeapotPhong>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_TEX_CUBE: rcode = render_typed<PipeTexCube>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_BLEND_TRIS: rcode = render_typed<PipeBlendTris>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_VOXEL_ICON: rcode = render_typed<PipeVoxelIcon>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_VERTEX_COLOR: rcode = render_typed<PipeVertexColor>(ctx, rc, prm, n_tiles); break;
+        default: rcode = EUC_E_INVALID;
+    }
+    // dd is pageable: make sure the async copy consumed it (render_typed synchronises; early outs do not)
+    return rcode;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int euc_abi_version(void) { return EUC_B200_ABI_VERSION; }
+
+int euc_init(int device_ordinal, euc_ctx** out_ctx) {
+    if (!out_ctx) return EUC_E_INVALID;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return EUC_E_CUDA;  // no CPU fallback
+    if (device_ordinal < 0 || device_ordinal >= n) return EUC_E_INVALID;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return EUC_E_CUDA;
+    euc_ctx* ctx = new euc_ctx();
+    ctx->dev = device_ordinal;
+    if (cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
+    ctx->stream = ctx->own;
+    if (cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->counters_host, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return EUC_E_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
+    *out_ctx = ctx;
+    return EUC_OK;
+}
+
+int euc_shutdown(euc_ctx* ctx) {
+    if (!ctx) return EUC_E_INVALID;
+    cudaSetDevice(ctx->dev);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->bufs) cudaFree(kv.second.d);
+    for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
+    Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx};
+    for (Scratch* s : ss) cudaFree(s->p);
+    cudaFree(ctx->counters);
+    cudaFreeHost(ctx->counters_host);
+    cudaStreamDestroy(ctx->own);
+    delete ctx;
+    return EUC_OK;
+}
+
+const char* euc_last_error(euc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int euc_set_stream(euc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return EUC_E_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+    return EUC_OK;
+}
+
+int euc_sync(euc_ctx* ctx) {
+    if (!ctx) return EUC_E_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EUC_OK;
+}
+
+int euc_set_stats(euc_ctx* ctx, int enabled) {
+    if (!ctx) return EUC_E_INVALID;
+    ctx->stats = enabled != 0;
+    return EUC_OK;
+}
+
+int euc_get_stats(euc_ctx* ctx, euc_render_stats* out) {
+    if (!ctx || !out) return EUC_E_INVALID;
+    CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->last.fragments = ctx->counters_host[1];
+    *out = ctx->last;
+    return EUC_OK;
+}
+
+int euc_buf_create(euc_ctx* ctx, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out) {
+    if (!ctx || !out) return EUC_E_INVALID;
+    if (texel_bytes != 4) return fail(ctx, EUC_E_UNSUPPORTED, "only 4-byte texels (u32 colour, f32 depth, RGBA8 texture) are supported");
+    if (layers == 0) return fail(ctx, EUC_E_INVALID, "layers must be >= 1");
+    CU(cudaSetDevice(ctx->dev));
+    Buf b;
+    b.w = width; b.h = height; b.layers = layers; b.texel = texel_bytes;
+    b.bytes = (size_t)width * height * layers * texel_bytes;  // Buffer::fill_with: len = product of sizes (buffer.rs:74-75)
+    if (b.bytes) CU(cudaMalloc(&b.d, b.bytes));
+    uint64_t hnd = ctx->next_handle++;
+    ctx->bufs[hnd] = b;
+    *out = hnd;
+    return EUC_OK;
+}
+
+int euc_buf_destroy(euc_ctx* ctx, euc_buf buf) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (it->second.d) CU(cudaFree(it->second.d));
+    ctx->bufs.erase(it);
+    return EUC_OK;
+}
+
+int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel) {
+    if (!ctx || !texel) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    const Buf& b = it->second;
+    const size_t n = b.bytes / 4;
+    if (n == 0) return EUC_OK;
+    uint32_t v;
+    std::memcpy(&v, texel, 4);
+    const size_t vec = (n + 3) / 4;
+    const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
+    fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)b.d, n, v);
+    CU(cudaGetLastError());
+    return EUC_OK;
+}
+
+int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes) {
+    if (!ctx || !host) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "upload of %zu bytes into a buffer of %zu bytes", bytes, it->second.bytes);
+    if (bytes) CU(cudaMemcpyAsync(it->second.d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return EUC_OK;
+}
+
+int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes) {
+    if (!ctx || !host) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "download of %zu bytes from a buffer of %zu bytes", bytes, it->second.bytes);
+    if (bytes) CU(cudaMemcpyAsync(host, it->second.d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EUC_OK;
+}
+
+int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes) {
+    if (!ctx || !out_ptr) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    *out_ptr = it->second.d;
+    if (out_bytes) *out_bytes = it->second.bytes;
+    return EUC_OK;
+}
+
+int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* layers) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    if (w) *w = it->second.w;
+    if (h) *h = it->second.h;
+    if (layers) *layers = it->second.layers;
+    return EUC_OK;
+}
+
+int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices, const uint32_t* indices,
+                    uint32_t n_indices, euc_geom* out) {
+    if (!ctx || !out || (!vertices && n_vertices) || vertex_stride == 0) return EUC_E_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    Geom g;
+    g.stride = vertex_stride; g.n_verts = n_vertices; g.n_idx = indices ? n_indices : 0;
+    const size_t vb = (size_t)vertex_stride * n_vertices;
+    CU(cudaMalloc((void**)&g.verts, std::max<size_t>(vb, 16)));
+    if (vb) CU(cudaMemcpyAsync(g.verts, vertices, vb, cudaMemcpyHostToDevice, ctx->stream));
+    if (indices) {
+        CU(cudaMalloc((void**)&g.idx, std::max<size_t>((size_t)n_indices * 4, 16)));
+        if (n_indices) CU(cudaMemcpyAsync(g.idx, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t hnd = ctx->next_handle++;
+    ctx->geoms[hnd] = g;
+    *out = hnd;
+    return EUC_OK;
+}
+
+int euc_geom_destroy(euc_ctx* ctx, euc_geom geom) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(it->second.verts));
+    if (it->second.idx) CU(cudaFree(it->second.idx));
+    ctx->geoms.erase(it);
+    return EUC_OK;
+}
+
+int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth, uint32_t row_begin,
+                         uint32_t row_end) {
+    if (!ctx || !desc) return EUC_E_INVALID;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    CU(cudaSetDevice(ctx->dev));
+    const Geom& g = it->second;
+    euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
+    RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end};
+    return render_common(ctx, rc);
+}
+
+int euc_render_geom(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth) {
+    return euc_render_geom_rows(ctx, desc, geom, pixel, depth, 0, 0xffffffffu);
+}
+
+int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices,
+               const uint32_t* indices, uint32_t n_indices, euc_buf pixel, euc_buf depth) {
+    if (!ctx || !desc || (!vertices && n_vertices) || vertex_stride == 0) return EUC_E_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    int rcode;
+    const size_t vb = (size_t)vertex_stride * n_vertices;
+    if ((rcode = ensure(ctx, ctx->tmp_verts, std::max<size_t>(vb, 16))) != EUC_OK) return rcode;
+    if (vb) CU(cudaMemcpyAsync(ctx->tmp_verts.p, vertices, vb, cudaMemcpyHostToDevice, ctx->stream));
+    Geom g;
+    g.verts = (uint8_t*)ctx->tmp_verts.p; g.stride = vertex_stride; g.n_verts = n_vertices;
+    if (indices) {
+        if ((rcode = ensure(ctx, ctx->tmp_idx, std::max<size_t>((size_t)n_indices * 4, 16))) != EUC_OK) return rcode;
+        if (n_indices) CU(cudaMemcpyAsync(ctx->tmp_idx.p, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
+        g.idx = (uint32_t*)ctx->tmp_idx.p; g.n_idx = n_indices;
+    }
+    euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
+    RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, 0, 0xffffffffu};
+    return render_common(ctx, rc);
+}
+
+int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_batch_draw* draws, uint32_t n_draws,
+                     const void* uniforms, euc_buf pixel, euc_buf depth) {
+    if (!ctx || !desc || (!draws && n_draws)) return EUC_E_INVALID;
+    if (n_draws == 0) return EUC_OK;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    CU(cudaSetDevice(ctx->dev));
+    RenderCall rc{desc, &it->second, draws, n_draws, uniforms, true, pixel, depth, 0, 0xffffffffu};
+    return render_common(ctx, rc);
+}
+
+}  // extern "C"

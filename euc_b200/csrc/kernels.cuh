@@ -1,0 +1,676 @@
+// kernels.cuh — sm_100a kernels of the raster back end.
+//
+//   K1+K2  setup_kernel<P>      vertex shade (per stream vertex, 128-bit loads) + primitive assembly + triangle
+//                               setup (src/pipeline.rs:273-289, src/index.rs:52-54, triangles.rs:54-173) + per-tile
+//                               population count.  One thread per triangle; emits a fixed-size setup record.
+//   K3     alloc_tiles_kernel   gives every non-empty 16x16 tile a private slice of the pair list
+//          fill_kernel          writes (tile <- triangle) pairs
+//          sort_lists_kernel    restores submission order inside every tile list (src/pipeline.rs:581 semantics)
+//   K4/K5  raster_kernel<P>     one warp per tile: lane = half a tile row (8 px); colour and depth of the tile live
+//                               in registers for the whole list; setup records stream into shared memory through
+//                               cp.async.bulk + mbarrier; coverage, depth test, fragment shade (incl. euc's
+//                               coarse-shading "MSAA"), blend in submission order (triangles.rs:219-303,
+//                               pipeline.rs:514-578).
+//   K7     fill_u32_kernel      Target::clear (buffer.rs:213-218)
+//
+// Bit-exactness notes (DESIGN.md §"Exactness"): the per-pixel weights are euc's *sequentially accumulated* chain
+// started at row_range[0] of the (triangle,row,band); lanes replay the chain up to their segment.
+#pragma once
+#include "shaders.cuh"
+
+namespace eucb {
+
+constexpr int TILE = 16;
+constexpr int REC_BASE_WORDS = 24;
+
+template <class P> struct RecLayout {
+    static constexpr int VPAD = (3 * P::V + 3) / 4 * 4;
+    static constexpr int WORDS = REC_BASE_WORDS + VPAD;
+    static constexpr int BYTES = WORDS * 4;
+};
+
+// Record word offsets
+enum : int {
+    R_O = 0,     // w_hom_origin[3]
+    R_DX = 3,    // w_hom_dx[3]
+    R_DY = 6,    // w_hom_dy[3]
+    R_ZH = 9,    // verts_hom[i][2]
+    R_VY = 12,   // verts_by_y: a.x a.y b.x b.y c.x c.y
+    R_BBX = 18,  // x0 | x1 << 16     (bounds clamped to [0, w])
+    R_BBY = 19,  // y0 | y1 << 16     (bounds clamped to [0, h]; per-band clamp happens per row)
+    R_FLAGS = 20,  // bit0: all three vertices pass the z clip
+    R_DRAW = 21,
+    R_VAR = 24
+};
+
+struct DrawDev {
+    uint32_t first, count;
+    int32_t base_vertex;
+    uint32_t layer;
+    uint32_t tri_begin;  // prefix of triangle counts
+    uint32_t n_tris;
+};
+
+struct Params {
+    // target
+    uint32_t w, h, layers;
+    uint32_t tiles_x, tiles_y;  // tiles per layer
+    uint32_t row_begin, row_end;  // rendered rows (multi-GPU bands); row_begin % 16 == 0
+    uint32_t group_rows;          // euc band height (pipeline.rs:329)
+    uint32_t msaa_level;
+    uint32_t* pixel;
+    float* depth;
+    // modes (pipeline.rs:178-209)
+    int32_t depth_test, depth_write, pixel_write, uses_depth;
+    int32_t zclip;
+    float zmin, zmax;
+    int32_t cull;
+    float flip_y;
+    // geometry
+    const uint8_t* vertices;
+    uint32_t vstride, n_vertices;
+    const uint32_t* indices;
+    const DrawDev* draws;
+    uint32_t n_draws;
+    uint32_t n_tris;
+    const uint8_t* uniforms;  // device array of n_draws blocks (batch) or nullptr -> uni_inline
+    uint32_t uniform_stride;
+    // intermediates
+    uint32_t* recs;
+    uint2* tri_bbox;
+    uint32_t* tile_count;   // zero on entry, zero again after fill
+    uint2* tile_range;      // (offset, n) per tile
+    uint32_t* tile_list;
+    uint32_t list_capacity;
+    unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
+    int32_t stats;
+    SamplerDev samp[EUC_MAX_SAMPLERS];
+    alignas(16) uint8_t uni_inline[320];
+};
+
+// -------------------------------------------------------------------------------------------------------
+// K7 clear
+// -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, size_t n, uint32_t v) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    uint4 vv = make_uint4(v, v, v, v);
+    for (; i + 4 <= n; i += stride) *reinterpret_cast<uint4*>(dst + i) = vv;
+    // tail (n % 4) handled by the last few threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n & ~(size_t)3) + threadIdx.x] = v;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// tile traversal shared by the count and fill passes
+// -------------------------------------------------------------------------------------------------------
+struct TileRect { uint32_t tx0, ty0, ntx, nty, layer_base; };
+
+__device__ __forceinline__ bool tile_rect(const Params& p, uint2 bb, uint32_t layer, TileRect& r) {
+    uint32_t x0 = bb.x & 0xffffu, x1 = bb.x >> 16, y0 = bb.y & 0xffffu, y1 = bb.y >> 16;
+    y0 = max(y0, p.row_begin);
+    y1 = min(y1, p.row_end);
+    if (x1 <= x0 || y1 <= y0) return false;
+    r.tx0 = x0 / TILE; r.ty0 = y0 / TILE;
+    r.ntx = (x1 - 1) / TILE - r.tx0 + 1;
+    r.nty = (y1 - 1) / TILE - r.ty0 + 1;
+    r.layer_base = layer * p.tiles_x * p.tiles_y;
+    return true;
+}
+
+// Calls op(tile_index, tri) for every tile of every lane's rectangle.  Small rectangles are walked by their own
+// lane; large ones (more than 8 tiles) are walked by the whole warp, one triangle at a time.
+template <class OP> __device__ __forceinline__ void for_each_tile(const Params& p, bool valid, const TileRect& r, uint32_t tri, OP op) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t nt = valid ? r.ntx * r.nty : 0u;
+    bool small = nt <= 8u;
+    if (valid && small) {
+        for (uint32_t j = 0; j < r.nty; ++j)
+            for (uint32_t i = 0; i < r.ntx; ++i) op(r.layer_base + (r.ty0 + j) * p.tiles_x + r.tx0 + i, tri);
+    }
+    uint32_t big = __ballot_sync(0xffffffffu, valid && !small);
+    while (big) {
+        int src = __ffs(big) - 1;
+        big &= big - 1;
+        uint32_t tx0 = __shfl_sync(0xffffffffu, r.tx0, src), ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
+        uint32_t ntx = __shfl_sync(0xffffffffu, r.ntx, src), n = __shfl_sync(0xffffffffu, nt, src);
+        uint32_t lb = __shfl_sync(0xffffffffu, r.layer_base, src), t = __shfl_sync(0xffffffffu, tri, src);
+        for (uint32_t i = lane; i < n; i += 32u) {
+            uint32_t j = i / ntx, k = i - j * ntx;
+            op(lb + (ty0 + j) * p.tiles_x + tx0 + k, t);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t find_draw(const Params& p, uint32_t tri) {
+    if (p.n_draws == 1) return 0;
+    uint32_t lo = 0, hi = p.n_draws - 1;  // last draw with tri_begin <= tri
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(&p.draws[mid].tri_begin) <= tri) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <class P> __device__ __forceinline__ const typename P::Uniforms& uniforms_of(const Params& p, uint32_t draw) {
+    const uint8_t* base = p.uniforms ? p.uniforms + (size_t)draw * p.uniform_stride : p.uni_inline;
+    return *reinterpret_cast<const typename P::Uniforms*>(base);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// K1 + K2: vertex shade, assemble, set up.  triangles.rs:54-173.
+// -------------------------------------------------------------------------------------------------------
+template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __grid_constant__ Params p) {
+    using L = RecLayout<P>;
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tri < p.n_tris;
+    uint2 bbox = make_uint2(0u, 0u);
+    uint32_t layer = 0;
+    bool oob = false;
+
+    if (live) {
+        const uint32_t d = find_draw(p, tri);
+        const DrawDev dr = p.draws[d];
+        layer = dr.layer;
+        const typename P::Uniforms& u = uniforms_of<P>(p, d);
+        const uint32_t s0 = dr.first + 3u * (tri - dr.tri_begin);
+
+        float hx[3], hy[3], hz[3], hw[3];
+        float var[3][P::V > 0 ? P::V : 1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            // index.rs:52-54: &verts[idx]; every stream element re-runs the vertex shader (no vertex cache)
+            long long vi = p.indices ? (long long)__ldg(p.indices + s0 + i) + dr.base_vertex : (long long)(s0 + i) + dr.base_vertex;
+            if (vi < 0 || vi >= (long long)p.n_vertices) { oob = true; vi = 0; }
+            float4 clip;
+            P::vertex(u, p.vertices + (size_t)vi * p.vstride, clip, var[i]);
+            hx[i] = clip.x * 1.0f;       // triangles.rs:61  (flip[0] == 1.0)
+            hy[i] = clip.y * p.flip_y;
+            hz[i] = clip.z;
+            hw[i] = clip.w;
+        }
+        // triangles.rs:64
+        float ex[3], ey[3], ez[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { ex[i] = hx[i] / hw[i]; ey[i] = hy[i] / hw[i]; ez[i] = hz[i] / hw[i]; }
+        // triangles.rs:67-70: cross(e1-e0, e2-e0).z
+        float ax = ex[1] - ex[0], ay = ey[1] - ey[0];
+        float bx = ex[2] - ex[0], by = ey[2] - ey[0];
+        float winding = ax * by - ay * bx;
+        bool culled = false;
+        if (p.cull != EUC_CULL_NONE) {
+            float cull_dir = p.cull == EUC_CULL_BACK ? 1.0f : -1.0f;
+            culled = winding * cull_dir < 0.0f;  // :73-77
+        }
+        if (oob) culled = true;
+        // :78-80 reverse vertex order when winding >= 0 (conditional swap of vertices 0 and 2)
+        const bool rev = !culled && winding >= 0.0f;
+        if (rev) {
+            float t;
+            t = hx[0]; hx[0] = hx[2]; hx[2] = t;  t = hy[0]; hy[0] = hy[2]; hy[2] = t;
+            t = hz[0]; hz[0] = hz[2]; hz[2] = t;  t = hw[0]; hw[0] = hw[2]; hw[2] = t;
+            t = ex[0]; ex[0] = ex[2]; ex[2] = t;  t = ey[0]; ey[0] = ey[2]; ey[2] = t;
+            t = ez[0]; ez[0] = ez[2]; ez[2] = t;
+        }
+
+        uint32_t* rec = p.recs + (size_t)tri * L::WORDS;
+        if (!culled) {
+            // :86-102 coords_to_weights
+            const float a0 = hx[0], a1 = hy[0], a3 = hw[0];
+            const float b0 = hx[1], b1 = hy[1], b3 = hw[1];
+            const float c0 = hx[2], c1 = hy[2], c2 = hw[2];  // c = [c.x, c.y, c.w]
+            const float ca0 = a0 - c0, ca1 = a1 - c1, ca2 = a3 - c2;
+            const float cb0 = b0 - c0, cb1 = b1 - c1, cb2 = b3 - c2;
+            // n = cross(ca, cb)
+            const float n0 = ca1 * cb2 - ca2 * cb1, n1 = ca2 * cb0 - ca0 * cb2, n2 = ca0 * cb1 - ca1 * cb0;
+            float rec_det = 1.0f;
+            if (n0 * n0 + n1 * n1 + n2 * n2 > 0.0f) rec_det = 1.0f / r_min(n0 * c0 + n1 * c1 + n2 * c2, -1.1920929e-07f);
+            // rows: cross(cb, c), cross(c, ca), n — each scaled by rec_det
+            float m[3][3];
+            m[0][0] = (cb1 * c2 - cb2 * c1) * rec_det; m[0][1] = (cb2 * c0 - cb0 * c2) * rec_det; m[0][2] = (cb0 * c1 - cb1 * c0) * rec_det;
+            m[1][0] = (c1 * ca2 - c2 * ca1) * rec_det; m[1][1] = (c2 * ca0 - c0 * ca2) * rec_det; m[1][2] = (c0 * ca1 - c1 * ca0) * rec_det;
+            m[2][0] = n0 * rec_det; m[2][1] = n1 * rec_det; m[2][2] = n2 * rec_det;
+            const float size_x = (float)p.w, size_y = (float)p.h;
+            const float sx = 2.0f / size_x, sy = -2.0f / size_y;  // to_ndc :44-48
+            float cw[3][3];  // matmul(m, to_ndc) :345-355, all nine products kept
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cw[i][0] = m[i][0] * sx + m[i][1] * 0.0f + m[i][2] * 0.0f;
+                cw[i][1] = m[i][0] * 0.0f + m[i][1] * sy + m[i][2] * 0.0f;
+                cw[i][2] = m[i][0] * -1.0f + m[i][1] * 1.0f + m[i][2] * 1.0f;
+            }
+            // :110-111 verts_screen
+            float scx[3], scy[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                scx[i] = size_x * (ex[i] * 0.5f + 0.5f);
+                scy[i] = size_y * (ey[i] * -0.5f + 0.5f);
+            }
+            // :114-139 bounds, clamped to the whole target here; the band clamp is applied per row in the raster kernel
+            const uint32_t bx0 = r_as_usize_clamped(r_min(r_min(scx[0], scx[1]), scx[2]) + 0.0f, 0u, p.w);
+            const uint32_t by0 = r_as_usize_clamped(r_min(r_min(scy[0], scy[1]), scy[2]) + 0.0f, 0u, p.h);
+            const uint32_t bx1 = r_as_usize_clamped(r_max(r_max(scx[0], scx[1]), scx[2]) + 1.0f, 0u, p.w);
+            const uint32_t by1 = r_as_usize_clamped(r_max(r_max(scy[0], scy[1]), scy[2]) + 1.0f, 0u, p.h);
+            // :142-145 finite-difference weight deltas
+            float o[3], wdx[3], wdy[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                o[i] = cw[i][0] * 0.0f + cw[i][1] * 0.0f + cw[i][2] * 1.0f;
+                float atx = cw[i][0] * 1000.0f + cw[i][1] * 0.0f + cw[i][2] * 1.0f;
+                float aty = cw[i][0] * 0.0f + cw[i][1] * 1000.0f + cw[i][2] * 1.0f;
+                wdx[i] = (atx - o[i]) * (1.0f / 1000.0f);
+                wdy[i] = (aty - o[i]) * (1.0f / 1000.0f);
+            }
+            // :148-171 order by y
+            const float min_y = r_min(r_min(scy[0], scy[1]), scy[2]);
+            int o0, o1, o2;
+            if (scy[0] == min_y) { if (scy[1] < scy[2]) { o0 = 0; o1 = 1; o2 = 2; } else { o0 = 0; o1 = 2; o2 = 1; } }
+            else if (scy[1] == min_y) { if (scy[0] < scy[2]) { o0 = 1; o1 = 0; o2 = 2; } else { o0 = 1; o1 = 2; o2 = 0; } }
+            else { if (scy[0] < scy[1]) { o0 = 2; o1 = 0; o2 = 1; } else { o0 = 2; o1 = 1; o2 = 0; } }
+            // :173 z clip classification
+            bool nvc = true;
+            if (p.zclip) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) nvc = nvc && (p.zmin <= ez[i] && ez[i] <= p.zmax);
+            }
+            bbox = make_uint2(bx0 | (bx1 << 16), by0 | (by1 << 16));
+
+            float4* r4 = reinterpret_cast<float4*>(rec);
+            r4[0] = make_float4(o[0], o[1], o[2], wdx[0]);
+            r4[1] = make_float4(wdx[1], wdx[2], wdy[0], wdy[1]);
+            r4[2] = make_float4(wdy[2], hz[0], hz[1], hz[2]);
+            const float sxs[3] = {scx[0], scx[1], scx[2]}, sys[3] = {scy[0], scy[1], scy[2]};
+            auto pick = [&](const float* a, int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]); };
+            r4[3] = make_float4(pick(sxs, o0), pick(sys, o0), pick(sxs, o1), pick(sys, o1));
+            r4[4] = make_float4(pick(sxs, o2), pick(sys, o2), __uint_as_float(bbox.x), __uint_as_float(bbox.y));
+            r4[5] = make_float4(__uint_as_float(nvc ? 1u : 0u), __uint_as_float(d), 0.0f, 0.0f);
+            if constexpr (P::V > 0) {
+                float flat[L::VPAD];
+#pragma unroll
+                for (int k = 0; k < L::VPAD; ++k) flat[k] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < P::V; ++k) flat[i * P::V + k] = (i == 1) ? var[1][k] : ((i == 0) != rev ? var[0][k] : var[2][k]);
+#pragma unroll
+                for (int k = 0; k < L::VPAD / 4; ++k) r4[6 + k] = make_float4(flat[4 * k], flat[4 * k + 1], flat[4 * k + 2], flat[4 * k + 3]);
+            }
+        }
+        p.tri_bbox[tri] = bbox;
+    }
+    if (__any_sync(0xffffffffu, oob) && oob) atomicOr(p.counters + 3, 1ull);
+
+    // per-tile population count
+    TileRect r;
+    bool valid = live && tile_rect(p, bbox, layer, r);
+    uint32_t npairs = 0;
+    for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
+    // total pairs (one atomic per warp)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
+    if ((threadIdx.x & 31u) == 0 && npairs) atomicAdd(p.counters + 0, (unsigned long long)npairs);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// K3: tile list allocation, fill, order restore
+// -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = t < n_tiles ? p.tile_count[t] : 0u;
+    // warp-aggregated allocation: one atomic per warp, tiles of a warp get adjacent slices
+    uint32_t lane = threadIdx.x & 31u, incl = n;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= (uint32_t)s) incl += v; }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(p.counters + 2, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (t < n_tiles) p.tile_range[t] = make_uint2((uint32_t)base + incl - n, n);
+}
+
+__global__ void __launch_bounds__(128) fill_kernel(const __grid_constant__ Params p) {
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tri < p.n_tris;
+    uint2 bbox = live ? p.tri_bbox[tri] : make_uint2(0u, 0u);
+    const uint32_t layer = live ? p.draws[find_draw(p, tri)].layer : 0u;
+    TileRect r;
+    bool valid = live && tile_rect(p, bbox, layer, r);
+    for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t t) {
+        uint32_t slot = atomicSub(p.tile_count + tile, 1u) - 1u;  // leaves tile_count zeroed for the next render
+        uint32_t off = p.tile_range[tile].x + slot;
+        if (off < p.list_capacity) p.tile_list[off] = t;
+    });
+}
+
+// One warp per tile.  Lists of up to 32 entries are sorted in registers (bitonic network over lanes); up to
+// SORT_SMEM entries in shared memory; longer ones in place in global memory.
+constexpr int SORT_SMEM = 2048;
+__device__ __forceinline__ void bitonic_mem(uint32_t* a, uint32_t n_pow2, uint32_t lane) {
+    for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < n_pow2; i += 32u) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__global__ void __launch_bounds__(128) sort_lists_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+    __shared__ uint32_t sm[4][SORT_SMEM];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * 4 + warp;
+    if (tile >= n_tiles) return;
+    const uint2 rg = p.tile_range[tile];
+    const uint32_t n = rg.y;
+    if (n <= 1) return;
+    uint32_t* list = p.tile_list + rg.x;
+    if (n <= 32) {
+        uint32_t v = lane < n ? list[lane] : 0xffffffffu;
+#pragma unroll
+        for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                bool up = (lane & k) == 0, lower = (lane & j) == 0;
+                v = (lower == up) ? min(v, o) : max(v, o);
+            }
+        }
+        if (lane < n) list[lane] = v;
+        return;
+    }
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= SORT_SMEM) {
+        uint32_t* a = sm[warp];
+        for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? list[i] : 0xffffffffu;
+        __syncwarp();
+        bitonic_mem(a, np2, lane);
+        for (uint32_t i = lane; i < n; i += 32u) list[i] = a[i];
+    } else {
+        // Global fallback: odd-even transposition is too slow; use bitonic with virtual padding (out-of-range = +inf).
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = lane; i < np2; i += 32u) {
+                    uint32_t ixj = i ^ j;
+                    if (ixj > i) {
+                        uint32_t x = i < n ? list[i] : 0xffffffffu, y = ixj < n ? list[ixj] : 0xffffffffu;
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { if (i < n) list[i] = y; if (ixj < n) list[ixj] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
+// -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// -------------------------------------------------------------------------------------------------------
+// K4 / K5: tile raster.
+// -------------------------------------------------------------------------------------------------------
+constexpr int RASTER_WARPS = 4;
+constexpr int BATCH = 8;  // setup records per bulk-copy stage
+
+template <class P> struct RasterSmem {
+    alignas(128) uint32_t rec[RASTER_WARPS][2][BATCH][RecLayout<P>::WORDS];
+    alignas(8) uint64_t bar[RASTER_WARPS][2];
+};
+
+// get_v_data (triangles.rs:274-294): closed-form weights at (x, y), perspective divide, weighted_sum3 (math.rs:38-40)
+template <class P> __device__ __forceinline__ void interpolate(const float* __restrict__ rec, float xf, float yf, float* var) {
+    const float wh0 = (rec[R_O + 0] + rec[R_DY + 0] * yf) + rec[R_DX + 0] * xf;
+    const float wh1 = (rec[R_O + 1] + rec[R_DY + 1] * yf) + rec[R_DX + 1] * xf;
+    const float wh2 = (rec[R_O + 2] + rec[R_DY + 2] * yf) + rec[R_DX + 2] * xf;
+    const float wu2 = wh2 - wh0 - wh1;
+    const float r = 1.0f / wh2;
+    const float w0 = wh0 * r, w1 = wh1 * r, w2 = wu2 * r;
+    const float* v0 = rec + R_VAR;
+    const float* v1 = v0 + P::V;
+    const float* v2 = v1 + P::V;
+#pragma unroll
+    for (int k = 0; k < P::V; ++k) var[k] = v0[k] * w0 + v1[k] * w1 + v2[k] * w2;
+}
+
+template <class P>
+__device__ __forceinline__ void shade_at(const typename P::Uniforms& u, const SamplerDev* samp, const float* rec, float xf, float yf, float* frag) {
+    float var[P::V > 0 ? P::V : 1];
+    interpolate<P>(rec, xf, yf, var);
+    P::fragment(u, samp, var, frag);
+}
+
+template <class P, bool MSAA> __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+    using L = RecLayout<P>;
+    __shared__ RasterSmem<P> sm;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
+    uint64_t* bar = sm.bar[warp];
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (tile >= n_tiles) return;
+    const uint2 rg = p.tile_range[tile];
+    const uint32_t n = rg.y;
+    if (n == 0) return;
+    const uint32_t* __restrict__ list = p.tile_list + rg.x;
+
+    // tile / lane geometry
+    const uint32_t tiles_per_layer = p.tiles_x * p.tiles_y;
+    const uint32_t layer = tile / tiles_per_layer;
+    const uint32_t tl = tile - layer * tiles_per_layer;
+    const uint32_t ty = tl / p.tiles_x, tx = tl - ty * p.tiles_x;
+    const uint32_t y = ty * TILE + (lane >> 1);
+    const uint32_t segx0 = tx * TILE + (lane & 1u) * 8u;
+    const bool row_ok = y < p.h && y >= p.row_begin && y < p.row_end;
+    const float yf = (float)y;
+    // euc band of this row (pipeline.rs:341-349): tgt_min.y = lo, tgt_max.y = hi
+    const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
+    const uint32_t band_hi = min(band_lo + p.group_rows, p.h);
+
+    const size_t layer_off = (size_t)layer * p.w * p.h;
+    float depth[8];
+    uint32_t color[8];
+    const bool full_seg = segx0 + 8u <= p.w;
+    {
+        const size_t base = layer_off + (size_t)y * p.w + segx0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { depth[j] = 0.0f; color[j] = 0u; }
+        if (row_ok && p.uses_depth) {
+            if (full_seg && (p.w & 3u) == 0) {
+                float4 a = *reinterpret_cast<const float4*>(p.depth + base), b = *reinterpret_cast<const float4*>(p.depth + base + 4);
+                depth[0] = a.x; depth[1] = a.y; depth[2] = a.z; depth[3] = a.w; depth[4] = b.x; depth[5] = b.y; depth[6] = b.z; depth[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) depth[j] = p.depth[base + j];
+            }
+        }
+        if (row_ok && p.pixel_write) {
+            if (full_seg && (p.w & 3u) == 0) {
+                uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
+                color[0] = a.x; color[1] = a.y; color[2] = a.z; color[3] = a.w; color[4] = b.x; color[5] = b.y; color[6] = b.z; color[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) color[j] = p.pixel[base + j];
+            }
+        }
+    }
+
+    uint32_t nfrag = 0;
+    const uint32_t n_batches = (n + BATCH - 1) / BATCH;
+    // stage 0: issue batch 0
+    auto issue = [&](uint32_t b, uint32_t id) {
+        // lanes [0, cnt) each copy one record of batch b; id = triangle index held by this lane
+        const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
+        uint64_t* mb = &bar[b & 1u];
+        if (lane == 0) mbar_expect_tx(mb, cnt * (uint32_t)L::BYTES);
+        __syncwarp();
+        if (lane < cnt) bulk_g2s(sm.rec[warp][b & 1u][lane], p.recs + (size_t)id * L::WORDS, (uint32_t)L::BYTES, mb);
+    };
+    uint32_t id_pf = lane < min((uint32_t)BATCH, n) ? __ldg(list + lane) : 0u;
+    issue(0, id_pf);
+    id_pf = (BATCH + lane < n && lane < BATCH) ? __ldg(list + BATCH + lane) : 0u;
+
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        // prefetch: records of batch b+1, ids of batch b+2
+        __syncwarp();  // all lanes finished reading stage (b+1)&1 in iteration b-1
+        if (b + 1 < n_batches) {
+            issue(b + 1, id_pf);
+            const uint32_t pos = (b + 2) * BATCH + lane;
+            id_pf = (lane < BATCH && pos < n) ? __ldg(list + pos) : 0u;
+        }
+        mbar_wait(&bar[b & 1u], (b >> 1) & 1u);
+        const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
+        for (uint32_t t = 0; t < cnt; ++t) {
+            const uint32_t* recu = sm.rec[warp][b & 1u][t];
+            const float* rec = reinterpret_cast<const float*>(recu);
+            const uint32_t bbx = recu[R_BBX], bby = recu[R_BBY];
+            const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
+            // lane-level reject: row outside bbox, segment outside bbox
+            if (!row_ok || y < y0 || y >= y1 || segx0 >= x1 || segx0 + 8u <= x0) continue;
+            // band-clamped vertical bounds (triangles.rs:114-139 with tgt_min/max of this row's band)
+            const uint32_t bymin = min(max(y0, band_lo), band_hi), bymax = min(max(y1, band_lo), band_hi);
+            const uint32_t extent = (x1 - x0) * (bymax - bymin);
+            uint32_t r0, r1;
+            if (extent < 128u) {  // :224-226
+                r0 = x0; r1 = x1;
+            } else {  // :228-253
+                const float a_x = rec[R_VY + 0], a_y = rec[R_VY + 1], b_x = rec[R_VY + 2], b_y = rec[R_VY + 3], c_x = rec[R_VY + 4], c_y = rec[R_VY + 5];
+                const float ac = a_x + ((yf - a_y) / (c_y - a_y)) * (c_x - a_x);
+                float lo, hi;
+                if (yf < b_y) {
+                    const float ab = a_x + ((yf - a_y) / (b_y - a_y)) * (b_x - a_x);
+                    lo = r_min(ab, ac); hi = r_max(ab, ac);
+                } else {
+                    const float bc = b_x + ((yf - b_y) / (c_y - b_y)) * (c_x - b_x);
+                    lo = r_min(bc, ac); hi = r_max(bc, ac);
+                }
+                const float e0 = floorf(lo), e1 = ceilf(hi);
+                const float fx0 = (float)x0, fx1 = (float)x1;
+                r0 = (e0 >= fx0 && e0 < fx1) ? __float2uint_rz(e0) : x0;
+                r1 = (e1 >= fx0 && e1 < fx1) ? __float2uint_rz(e1) : x1;
+            }
+            if (segx0 >= r1 || segx0 + 8u <= r0 || r1 <= r0) continue;
+            // chain start (:257-260) and replay up to this lane's segment (:301)
+            const float dx0 = rec[R_DX + 0], dx1 = rec[R_DX + 1], dx2 = rec[R_DX + 2];
+            const float r0f = (float)r0;
+            float w0 = (rec[R_O + 0] + rec[R_DY + 0] * yf) + dx0 * r0f;
+            float w1 = (rec[R_O + 1] + rec[R_DY + 1] * yf) + dx1 * r0f;
+            float w2 = (rec[R_O + 2] + rec[R_DY + 2] * yf) + dx2 * r0f;
+            if (segx0 > r0) {
+                const uint32_t npre = segx0 - r0;
+#pragma unroll 4
+                for (uint32_t i = 0; i < npre; ++i) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }
+            }
+            const float z0 = rec[R_ZH + 0], z1 = rec[R_ZH + 1], z2 = rec[R_ZH + 2];
+            const bool nvc = (recu[R_FLAGS] & 1u) != 0u;
+            const typename P::Uniforms& u = uniforms_of<P>(p, recu[R_DRAW]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t x = segx0 + (uint32_t)j;
+                const bool inr = x >= r0 && x < r1;
+                const float wu2 = w2 - w0 - w1;                          // :264
+                if (inr && w0 >= 0.0f && w1 >= 0.0f && wu2 >= 0.0f) {    // :267
+                    const float z = z0 * w0 + z1 * w1 + z2 * wu2;        // :269
+                    bool pass = nvc || !p.zclip || (p.zmin <= z && z <= p.zmax);  // :271
+                    if (pass && p.depth_test != EUC_DEPTH_NONE) {        // pipeline.rs:519-526
+                        const float old_z = depth[j];
+                        pass = p.depth_test == EUC_DEPTH_LESS ? (z < old_z) : (p.depth_test == EUC_DEPTH_EQUAL ? (z == old_z) : (z > old_z));
+                    }
+                    if (pass) {
+                        ++nfrag;
+                        if (p.depth_write) depth[j] = z;                 // pipeline.rs:536-538
+                        if (P::HAS_FRAGMENT && p.pixel_write) {          // pipeline.rs:540-577
+                            float frag[4];
+                            if (!MSAA) {
+                                shade_at<P>(u, p.samp, rec, (float)x, yf, frag);
+                            } else {
+                                const uint32_t Lv = p.msaa_level;
+                                const float msaa_div = 1.0f / (float)(1u << Lv);
+                                const uint32_t rx = x, ry = y - band_lo;  // x - tgt_min[0], y - tgt_min[1]
+                                const float fractx = r_fract((float)rx * msaa_div), fracty = r_fract((float)ry * msaa_div);
+                                const uint32_t posix = rx >> Lv, posiy = ry >> Lv;
+                                const float cx0 = (float)((posix + 0u) << Lv), cx1 = (float)((posix + 1u) << Lv);
+                                const float cy0 = (float)(band_lo + ((posiy + 0u) << Lv)), cy1 = (float)(band_lo + ((posiy + 1u) << Lv));
+                                float t00[4], t10[4], t01[4], t11[4];
+                                shade_at<P>(u, p.samp, rec, cx0, cy0, t00);
+                                shade_at<P>(u, p.samp, rec, cx1, cy0, t10);
+                                shade_at<P>(u, p.samp, rec, cx0, cy1, t01);
+                                shade_at<P>(u, p.samp, rec, cx1, cy1, t11);
+                                const float omy = 1.0f - fracty, omx = 1.0f - fractx;
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const float t0 = t00[c] * omy + t01[c] * fracty;
+                                    const float t1 = t10[c] * omy + t11[c] * fracty;
+                                    frag[c] = t0 * omx + t1 * fractx;
+                                }
+                            }
+                            color[j] = P::blend(color[j], frag);
+                        }
+                    }
+                }
+                if (x >= r0) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }  // :301
+            }
+        }
+    }
+
+    // write back
+    if (row_ok) {
+        const size_t base = layer_off + (size_t)y * p.w + segx0;
+        if (p.depth_write) {
+            if (full_seg && (p.w & 3u) == 0) {
+                *reinterpret_cast<float4*>(p.depth + base) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+                *reinterpret_cast<float4*>(p.depth + base + 4) = make_float4(depth[4], depth[5], depth[6], depth[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.depth[base + j] = depth[j];
+            }
+        }
+        if (P::HAS_FRAGMENT && p.pixel_write) {
+            if (full_seg && (p.w & 3u) == 0) {
+                *reinterpret_cast<uint4*>(p.pixel + base) = make_uint4(color[0], color[1], color[2], color[3]);
+                *reinterpret_cast<uint4*>(p.pixel + base + 4) = make_uint4(color[4], color[5], color[6], color[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.pixel[base + j] = color[j];
+            }
+        }
+    }
+    if (p.stats) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) nfrag += __shfl_xor_sync(0xffffffffu, nfrag, s);
+        if (lane == 0 && nfrag) atomicAdd(p.counters + 1, (unsigned long long)nfrag);
+    }
+}
+
+}  // namespace eucb

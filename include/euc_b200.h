@@ -1,0 +1,211 @@
+/*
+ * euc_b200.h — C ABI of the B200-native raster back end for euc's `Pipeline::render` hot path.
+ *
+ * Every entry point returns `int`: 0 = EUC_OK, < 0 = EUC_E_*.  A human-readable message for the last
+ * failure on a context is available through euc_last_error().  Nothing here unwinds, aborts or prints.
+ * Host pointers are borrowed for the duration of the call only.  Device buffers are owned by the
+ * context and named by opaque 64-bit handles (0 is never a valid handle: it stands for euc's
+ * `Empty` target, reference src/texture.rs:285-319).
+ *
+ * What each entry point replaces in the reference (paths relative to the euc crate root):
+ *
+ *   euc_buf_create / euc_buf_destroy   Buffer2d::fill / drop              src/buffer.rs:60-83
+ *   euc_buf_clear                      Target::clear                      src/buffer.rs:213-218
+ *   euc_buf_upload / euc_buf_download  Buffer::raw_mut / Buffer::raw      src/buffer.rs:104-114
+ *   euc_geom_create / euc_geom_destroy the vertex slice + IndexedVertices src/index.rs:4-55
+ *   euc_render / euc_render_geom       Pipeline::render                   src/pipeline.rs:248-300
+ *                                      (+ render_par :304-366, render_inner :396-614,
+ *                                         Triangles::rasterize src/rasterizer/triangles.rs:15-306,
+ *                                         Lines::rasterize src/rasterizer/lines.rs:12-120)
+ *   euc_render_batch                   a loop of Pipeline::render calls over independent targets
+ *   euc_pipeline_desc                  the trait getters pixel_mode/depth_mode/coordinate_mode/aa_mode/
+ *                                      rasterizer_config                  src/pipeline.rs:178-209
+ *   euc_sampler_desc                   Texture::linear()/nearest() + Sampler::clamped()/tiled()/mirrored()
+ *                                                                         src/texture.rs:51-95, src/sampler/mod.rs:44-70
+ *
+ * The reference is generic over user closures (vertex/fragment/blend).  A device back end cannot call
+ * host closures per fragment, so the shader stages of the benchmarked pipelines exist as CUDA device
+ * functions selected by `pipeline_id`; their uniform blocks are the POD structs below.
+ */
+#ifndef EUC_B200_H
+#define EUC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EUC_B200_ABI_VERSION 1
+
+typedef struct euc_ctx euc_ctx;
+typedef uint64_t euc_buf;  /* device Buffer2d handle; 0 == euc `Empty` target */
+typedef uint64_t euc_geom; /* device-resident vertex (+ optional index) buffer */
+
+enum euc_status {
+    EUC_OK = 0,
+    EUC_E_INVALID = -1,       /* bad argument / unknown handle / malformed desc */
+    EUC_E_SIZE_MISMATCH = -2, /* reference: assert_eq!(pixel.size(), depth.size()) src/pipeline.rs:262-266 */
+    EUC_E_UNSUPPORTED = -3,   /* e.g. width > 20000 (reference divides by zero, src/pipeline.rs:329-330) */
+    EUC_E_CUDA = -4,          /* CUDA runtime failure, message is sticky */
+    EUC_E_OOM = -5,
+    EUC_E_OUT_OF_BOUNDS = -6  /* index >= n_vertices (reference: slice index panic, src/index.rs:53) */
+};
+
+/* Shader-stage sets.  Each one is the CUDA restatement of a concrete `impl Pipeline`. */
+enum euc_pipeline_id {
+    EUC_PIPE_TEAPOT_SHADOW = 0, /* benches/teapot.rs:10-51   depth-only shadow pass            */
+    EUC_PIPE_TEAPOT_PHONG = 1,  /* benches/teapot.rs:53-142  Phong + shadow-map lookup         */
+    EUC_PIPE_TEX_CUBE = 2,      /* examples/texture_mapping.rs:5-35  sampler lookup            */
+    EUC_PIPE_BLEND_TRIS = 3,    /* BASELINE config 4: pre-transformed rgba triangles, src-over */
+    EUC_PIPE_VOXEL_ICON = 4,    /* BASELINE config 5: lit voxel meshes, src-over               */
+    EUC_PIPE_VERTEX_COLOR = 5,  /* examples/triangle.rs:7-25, examples/spinning_cube.rs:5-29   */
+    EUC_PIPE_COUNT = 6
+};
+
+enum euc_primitive_kind { /* src/primitives.rs:21, :82, :49 */
+    EUC_PRIM_TRIANGLE_LIST = 0,
+    EUC_PRIM_LINE_LIST = 1,
+    EUC_PRIM_LINE_TRIANGLE_LIST = 2
+};
+
+enum euc_cull_mode { EUC_CULL_NONE = 0, EUC_CULL_BACK = 1, EUC_CULL_FRONT = 2 }; /* src/rasterizer/mod.rs:10-18 */
+
+/* DepthMode.test : Option<Ordering>  (src/pipeline.rs:14-19) */
+enum euc_depth_test { EUC_DEPTH_NONE = 0, EUC_DEPTH_LESS = 1, EUC_DEPTH_EQUAL = 2, EUC_DEPTH_GREATER = 3 };
+
+enum euc_handedness { EUC_HAND_LEFT = 0, EUC_HAND_RIGHT = 1 }; /* stored, never read by the rasterisers */
+
+enum euc_filter { EUC_FILTER_NEAREST = 0, EUC_FILTER_LINEAR = 1 };                      /* src/sampler/{nearest,linear}.rs */
+enum euc_wrap { EUC_WRAP_NONE = 0, EUC_WRAP_CLAMP = 1, EUC_WRAP_TILE = 2, EUC_WRAP_MIRROR = 3 }; /* src/sampler/mod.rs:100-179 */
+
+enum euc_texel_format {
+    EUC_TEXEL_F32 = 0,         /* Buffer2d<f32> sampled as f32 (shadow map)                               */
+    EUC_TEXEL_RGBA8_TO_F32 = 1 /* Buffer2d<[u8;4]>.map(|p| p as f32): 0..255, not normalised (texture.rs:140-176) */
+};
+
+typedef struct euc_sampler_desc {
+    euc_buf buf; /* device buffer bound as texture; 0 = unbound */
+    int32_t format; /* euc_texel_format */
+    int32_t filter; /* euc_filter */
+    int32_t wrap;   /* euc_wrap */
+    int32_t _pad;
+} euc_sampler_desc;
+
+#define EUC_MAX_SAMPLERS 2
+
+/* POD mirror of the `Pipeline` trait getters (src/pipeline.rs:178-209) plus the pipeline's uniform state. */
+typedef struct euc_pipeline_desc {
+    int32_t pipeline_id;    /* euc_pipeline_id */
+    int32_t primitive_kind; /* euc_primitive_kind (type Primitives) */
+    int32_t cull_mode;      /* rasterizer_config(): euc_cull_mode */
+    int32_t depth_test;     /* depth_mode().test: euc_depth_test */
+    int32_t depth_write;    /* depth_mode().write */
+    int32_t pixel_write;    /* pixel_mode().write */
+    int32_t y_axis_up;      /* coordinate_mode().y_axis_direction == Up */
+    int32_t handedness;     /* coordinate_mode().handedness */
+    int32_t z_clip_enabled; /* coordinate_mode().z_clip_range.is_some() */
+    float z_clip_min;       /* inclusive (src/pipeline.rs:151-156) */
+    float z_clip_max;       /* inclusive */
+    int32_t msaa_level;     /* aa_mode(): 0 = AaMode::None, n = Msaa{level:n}; clamped to 0..6 (src/pipeline.rs:291-294) */
+    const void* uniforms;   /* host pointer to the pipeline's uniform block (structs below) */
+    uint32_t uniform_bytes;
+    uint32_t _pad;
+    euc_sampler_desc samplers[EUC_MAX_SAMPLERS];
+} euc_pipeline_desc;
+
+/* ---- uniform blocks and vertex layouts (all matrices column-major, like vek::Mat4) ------------------ */
+
+/* EUC_PIPE_TEAPOT_SHADOW: vertex = euc_vertex_pn. */
+typedef struct euc_uniforms_teapot_shadow { float mvp[16]; } euc_uniforms_teapot_shadow;
+
+/* EUC_PIPE_TEAPOT_PHONG: vertex = euc_vertex_pn; sampler 0 = shadow map (F32, LINEAR, CLAMP in the bench). */
+typedef struct euc_uniforms_teapot_phong {
+    float m[16], v[16], p[16], light_vp[16];
+    float light_pos[4]; /* xyz used */
+    float cam_pos[4];   /* xyz used */
+} euc_uniforms_teapot_phong;
+
+/* EUC_PIPE_TEX_CUBE: vertex = euc_vertex_p4uv; sampler 0 = colour texture. */
+typedef struct euc_uniforms_tex_cube { float mvp[16]; } euc_uniforms_tex_cube;
+
+/* EUC_PIPE_BLEND_TRIS: vertex = euc_vertex_p4c4 with `pos` already in clip space; no uniforms. */
+
+/* EUC_PIPE_VOXEL_ICON: vertex = euc_vertex_voxel. */
+typedef struct euc_uniforms_voxel_icon {
+    float mvp[16];
+    float light_dir[4]; /* xyz used, unit length */
+} euc_uniforms_voxel_icon;
+
+/* EUC_PIPE_VERTEX_COLOR: vertex = euc_vertex_p4c4. */
+typedef struct euc_uniforms_vertex_color { float mvp[16]; } euc_uniforms_vertex_color;
+
+typedef struct euc_vertex_pn { float pos[3]; float normal[3]; } euc_vertex_pn;                     /* 24 B */
+typedef struct euc_vertex_p4uv { float pos[4]; float uv[2]; float _pad[2]; } euc_vertex_p4uv;     /* 32 B */
+typedef struct euc_vertex_p4c4 { float pos[4]; float rgba[4]; } euc_vertex_p4c4;                  /* 32 B */
+typedef struct euc_vertex_voxel { float pos[3]; float normal[3]; uint8_t rgba[4]; uint32_t _pad; } euc_vertex_voxel; /* 32 B */
+
+/* One draw of a batch (euc_render_batch): an index/vertex range of a geom, its own uniforms and targets. */
+typedef struct euc_batch_draw {
+    uint32_t first;       /* first index (indexed geom) or first vertex (non-indexed) */
+    uint32_t count;       /* number of stream vertices; a trailing partial primitive is dropped (pipeline.rs:283) */
+    int32_t base_vertex;  /* added to every index */
+    uint32_t layer;       /* target layer inside the pixel/depth buffer arrays */
+} euc_batch_draw;
+
+/* Per-render statistics (device counters read back on request). */
+typedef struct euc_render_stats {
+    uint64_t primitives;      /* assembled primitives */
+    uint64_t binned_pairs;    /* (tile, primitive) pairs produced by the binner */
+    uint64_t fragments;       /* emit_fragment calls (depth-test passes), as the reference counts them */
+} euc_render_stats;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int euc_abi_version(void);
+int euc_init(int device_ordinal, euc_ctx** out_ctx);
+int euc_shutdown(euc_ctx* ctx);
+const char* euc_last_error(euc_ctx* ctx);
+/* Run all subsequent work of this context on `cuda_stream` (a cudaStream_t / CUstream); NULL = the context's own stream. */
+int euc_set_stream(euc_ctx* ctx, void* cuda_stream);
+int euc_sync(euc_ctx* ctx);
+/* Enable (1) / disable (0) fragment counting; counting costs one atomic per warp per tile. */
+int euc_set_stats(euc_ctx* ctx, int enabled);
+int euc_get_stats(euc_ctx* ctx, euc_render_stats* out); /* blocking; stats of the last render call */
+
+/* ---- Buffer2d --------------------------------------------------------------------------------------- */
+/* `layers` > 1 creates an array of equally sized targets stored back to back (batch rendering). texel_bytes: 4. */
+int euc_buf_create(euc_ctx* ctx, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out);
+int euc_buf_destroy(euc_ctx* ctx, euc_buf buf);
+int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel);                     /* all layers */
+int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes);       /* row-major, x + w*y, layer-major */
+int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes);           /* blocking */
+int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes);
+int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* layers);
+
+/* ---- geometry --------------------------------------------------------------------------------------- */
+/* indices may be NULL (non-indexed stream). Indices are u32 on the device (the reference uses usize). */
+int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices,
+                    const uint32_t* indices, uint32_t n_indices, euc_geom* out);
+int euc_geom_destroy(euc_ctx* ctx, euc_geom geom);
+
+/* ---- render ----------------------------------------------------------------------------------------- */
+/* Pipeline::render with host geometry: uploads, renders, returns without waiting for the device. */
+int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices, uint32_t vertex_stride,
+               uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, euc_buf pixel, euc_buf depth);
+/* Pipeline::render with device-resident geometry. */
+int euc_render_geom(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth);
+/* Row-restricted render: only target rows [row_begin, row_end) are produced (screen-space bands for
+ * multi-GPU partitioning). The rows written are bit-identical to the same rows of a full render because
+ * euc's row bands are independent (src/pipeline.rs:348-350). row_begin must be a multiple of 16. */
+int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth,
+                         uint32_t row_begin, uint32_t row_end);
+/* n_draws independent renders in one launch sequence. `uniforms` holds n_draws blocks of
+ * desc->uniform_bytes each (desc->uniforms is ignored). Draw i renders into layer draws[i].layer. */
+int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_batch_draw* draws,
+                     uint32_t n_draws, const void* uniforms, euc_buf pixel, euc_buf depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EUC_B200_H */
