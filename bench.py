@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of euc's `Pipeline::render` hot path on B200 (and of the CPU restatement beside it).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c1|c2|c3|c5] [--impl ours|reference]
+  torchrun ... bench.py --gpus N ...        (one rank per GPU; NCCL)
+
+A "step" is one frame: clears + every pass of the workload.  Default workload = BASELINE config 4
+("C4": 2^20-triangle indexed TriangleList, random depth + alpha blend, 3840x2160), the configuration the
+north star's target is quoted on.  At N > 1 the C4 frame is split into screen-space row bands (one per rank, tile
+aligned) and the colour rows are all-gathered over NCCL ("strong" scaling); C5 shards independent icon frames
+across ranks with no collective ("weak").
+
+value = whole-job frames/s with geometry and targets resident in HBM.
+e2e   = frames/s through the host-facing call: per step the geometry is copied host->device from pinned memory and
+        the finished colour buffer is read back device->host.
+roofline = raster kernel: algorithmic bytes per frame / its mean launch duration (CUDA events around the
+        launch, inside the timed region) against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline = the C++ restatement of euc's render_par (oracle/, all host cores) on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--icons", type=int, default=4096, help="C5: icons in the whole job")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workload definitions shared by both arms
+# ---------------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    "c1": dict(name="C1 teapot shadow(512^2)+phong 640x480", w=640, h=480, shadow=512, msaa=0),
+    "c2": dict(name="C2 textured cube bilinear+tiled 1920x1080", w=1920, h=1080),
+    "c3": dict(name="C3 teapot shadow(2048^2)+phong 3840x2160 msaa level 1", w=3840, h=2160, shadow=2048, msaa=1),
+    "c4": dict(name="C4 2^20-triangle indexed TriangleList, random depth + alpha blend, 3840x2160", w=3840, h=2160, quads=1 << 19),
+    "c5": dict(name="C5 voxel-icon batch 256x256, depth + blend", w=256, h=256),
+}
+
+
+def algorithmic_bytes(wl, args, scene):
+    """compulsory I/O, every byte once: indices + vertices + sampled textures + written targets."""
+    c = WORKLOADS[wl]
+    w, h = c["w"], c["h"]
+    if wl in ("c1", "c3"):
+        s = c["shadow"]
+        vb = scene["stream"].nbytes  # 6768 * 24
+        return vb + s * s * 4 + vb + s * s * 4 + w * h * 8
+    if wl == "c2":
+        return scene["idx"].nbytes + scene["verts"].nbytes + scene["tex"].nbytes + w * h * 4
+    if wl == "c4":
+        return scene["idx"].nbytes + scene["verts"].nbytes + w * h * 8
+    if wl == "c5":
+        return scene["idx"].nbytes + scene["verts"].nbytes + scene["n_icons"] * w * h * 8
+    raise ValueError(wl)
+
+
+def build_scene(wl, args, rank=0, world=1):
+    from euc_b200 import scenes
+    c = WORKLOADS[wl]
+    if wl in ("c1", "c3"):
+        return dict(stream=scenes.teapot_stream(), u=scenes.teapot_uniforms(c["w"], c["h"], c["shadow"]))
+    if wl == "c2":
+        verts, idx = scenes.cube_geometry(uv_scale=3.0)
+        return dict(verts=verts, idx=idx, tex=scenes.rust_texture(), mvp=scenes.cube_mvp(250, c["w"], c["h"]))
+    if wl == "c4":
+        verts, idx = scenes.blend_tris(c["quads"], c["w"], c["h"])
+        return dict(verts=verts, idx=idx)
+    if wl == "c5":
+        per = args.icons // world
+        verts, idx, draws, ubs = scenes.voxel_icon_batch(per, first_icon=rank * per)
+        return dict(verts=verts, idx=idx, draws=draws, ubs=ubs, n_icons=per)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), during the timed regions
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the C++ restatement of euc (oracle/) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_frame(wl, scene, rows=None, threads=0):
+    """One frame of `wl` on the oracle (clears + all passes).  Returns (seconds, fragments).  rows=(r0, r1) restricts
+    the final pass to the euc bands intersecting those rows (bounded sample)."""
+    import euc_b200 as e
+    from oracle import oracle
+    c = WORKLOADS[wl]
+    w, h = c["w"], c["h"]
+    t0 = time.perf_counter()
+    frags = 0
+    if wl in ("c1", "c3"):
+        s, u = c["shadow"], scene["u"]
+        shadow = np.empty((s, s), np.float32); shadow.fill(1.0)
+        color = np.zeros((h, w), np.uint32)
+        depth = np.empty((h, w), np.float32); depth.fill(1.0)
+        frags += oracle.render(e.TeapotShadow(u["shadow_mvp"]), scene["stream"], None, shadow, n_threads=threads)["fragments"]
+        aa = e.AaMode.Msaa(c["msaa"]) if c["msaa"] else None
+        frags += oracle.render(e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], e.Sampler(shadow, e.abi.TEXEL_F32, e.abi.FILTER_LINEAR).clamped(),
+                                        u["light_vp"], u["cam_pos"], aa=aa), scene["stream"], color, depth, n_threads=threads, rows=rows)["fragments"]
+    elif wl == "c2":
+        color = np.empty((h, w), np.uint32); color.fill(180)
+        t = scene["tex"]
+        smp = e.Sampler(t.view(np.uint32).reshape(t.shape[0], t.shape[1]), e.abi.TEXEL_RGBA8_TO_F32, e.abi.FILTER_LINEAR).tiled()
+        frags += oracle.render(e.Cube(scene["mvp"], smp), e.IndexedVertices(scene["idx"], scene["verts"]), color, None, n_threads=threads, rows=rows)["fragments"]
+    elif wl == "c4":
+        color = np.empty((h, w), np.uint32); color.fill(0xFF000000)
+        depth = np.empty((h, w), np.float32); depth.fill(1.0)
+        frags += oracle.render(e.BlendTris(), e.IndexedVertices(scene["idx"], scene["verts"]), color, depth, n_threads=threads, rows=rows)["fragments"]
+    elif wl == "c5":
+        from euc_b200 import scenes
+        iv = e.IndexedVertices(scene["idx"], scene["verts"])
+        n = scene["n_icons"] if rows is None else rows
+        for k in range(n):
+            color = np.zeros((h, w), np.uint32)
+            depth = np.empty((h, w), np.float32); depth.fill(1.0)
+            first, count, base, _ = scene["draws"][k]
+            ub = np.frombuffer(scene["ubs"], dtype=np.float32).reshape(-1, 20)[k]
+            frags += oracle.render(e.VoxelIcon(ub[:16].reshape(4, 4).T, ub[16:19]), iv, color, depth, n_threads=threads, draw=(first, count, base))["fragments"]
+    return time.perf_counter() - t0, frags
+
+
+def cpu_plan(wl, scene, budget_s=10.0):
+    """Chooses a bounded sample of the frame for the CPU arm.  Returns (run, scale, description, cores): run() renders
+    the sample once and returns seconds; one frame costs about run() * scale seconds."""
+    from oracle import oracle
+    cores = oracle.hardware_concurrency()
+    c = WORKLOADS[wl]
+    h = c["h"]
+    if wl == "c5":
+        n = min(scene["n_icons"], 64)
+        return (lambda: cpu_frame(wl, scene, rows=n)[0]), 1.0 / n, f"{n} icons of the batch, one after another, each by euc's band threads", cores
+    if wl in ("c1", "c2"):
+        return (lambda: cpu_frame(wl, scene)[0]), 1.0, "one full frame", cores
+    # big frames: probe 1/8 of the rows (doubles as warm-up), take the whole frame if it fits the budget
+    r1 = (h // 8) // 80 * 80
+    t8, _ = cpu_frame(wl, scene, rows=(0, r1))
+    if t8 * h / r1 <= budget_s:
+        return (lambda: cpu_frame(wl, scene)[0]), 1.0, "one full frame", cores
+    return ((lambda: cpu_frame(wl, scene, rows=(0, r1))[0]), h / r1,
+            f"the euc bands covering rows [0,{r1}) of {h} (every band walks all primitives), scaled by {h}/{r1}", cores)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl = args.workload
+    steps = args.steps if args.steps is not None else 3
+    warm = args.warmup if args.warmup is not None else 1
+    scene = build_scene(wl, args)
+    run, scale, desc, cores = cpu_plan(wl, scene, budget_s=6.0)
+    t_budget = time.perf_counter() + 150.0  # keep the whole arm within a few minutes
+    for _ in range(warm):
+        run()
+        if time.perf_counter() > t_budget:
+            break
+    times = []
+    for _ in range(steps):
+        times.append(run())
+        if time.perf_counter() > t_budget:
+            break
+    sec_per_frame = float(np.mean(times)) * scale
+    value = 1.0 / sec_per_frame
+    line = {
+        "impl": "reference", "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm, "ms_per_step": 1000.0 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak" if wl == "c5" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl]["name"], "target": f"{WORKLOADS[wl]['w']}x{WORKLOADS[wl]['h']}",
+                   "note": "C++ restatement of euc's render_par (rustc unavailable here), all host cores; each step is the bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import euc_b200 as e
+
+    wl = args.workload
+    c = WORKLOADS[wl]
+    w, h = c["w"], c["h"]
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = e.Context(local_rank)
+    stream = torch.cuda.Stream()  # a real (non-default) stream: shared by torch ops, NCCL waits and the raster library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    scene = build_scene(wl, args, rank, world)
+    steps = args.steps if args.steps is not None else {"c4": 100, "c3": 100, "c5": 10}.get(wl, 300)
+    warm = max(3, args.warmup if args.warmup is not None else 5)
+
+    h2d = d2h = 0
+    frags_per_frame = None
+    keep = []
+
+    if wl == "c4":
+        # row partition: tile rows (16 px) split evenly; every rank owns one contiguous slot of the gather buffer
+        tile_rows = (h + 15) // 16
+        per = (tile_rows + world - 1) // world
+        slot_rows = per * 16
+        r0, r1 = min(rank * slot_rows, h), min((rank + 1) * slot_rows, h)
+        gather = torch.empty(world * slot_rows * w, dtype=torch.int32, device="cuda")
+        color = e.Buffer2d.wrap(gather.data_ptr(), [w, h], np.uint32, ctx)
+        depth = e.Buffer2d([w, h], np.float32, ctx)
+        geom = e.Geometry(scene["verts"], scene["idx"], ctx)
+        pipe = e.BlendTris()
+        pv = torch.from_numpy(scene["verts"].view(np.uint8)).pin_memory()
+        pi = torch.from_numpy(scene["idx"].view(np.uint8)).pin_memory()
+        host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
+        my_slot = gather[rank * slot_rows * w:(rank + 1) * slot_rows * w]
+        keep += [pv, pi, host_out, gather]
+
+        def frame():
+            color.clear(0xFF000000)
+            depth.clear(1.0)
+            pipe.render(geom, color, depth, rows=(r0, r1))
+            if world > 1:
+                dist.all_gather_into_tensor(gather, my_slot)
+
+        def frame_e2e():
+            geom.update(pv.data_ptr(), pi.data_ptr())
+            frame()
+            if rank == 0:
+                host_out.copy_(gather[: h * w], non_blocking=True)
+
+        h2d, d2h = pv.numel() + pi.numel(), h * w * 4
+        config_extra = {"partition": f"{world} row band(s) of {slot_rows} rows + NCCL all_gather of colour rows" if world > 1 else "single GPU",
+                        "l2": "working set (80 MB geometry + 151 MB setup records + 66 MB targets) > 126 MB L2; no flush"}
+    elif wl in ("c1", "c3"):
+        s, u = c["shadow"], scene["u"]
+        geom = e.Geometry(scene["stream"], None, ctx)
+        shadow = e.Buffer2d([s, s], np.float32, ctx)
+        color = e.Buffer2d([w, h], np.uint32, ctx)
+        depth = e.Buffer2d([w, h], np.float32, ctx)
+        aa = e.AaMode.Msaa(c["msaa"]) if c["msaa"] else None
+        p1 = e.TeapotShadow(u["shadow_mvp"])
+        p2 = e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"], aa=aa)
+        pv = torch.from_numpy(scene["stream"].view(np.uint8)).pin_memory()
+        host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
+        cptr, _ = color.device_ptr()
+        keep += [pv, host_out]
+
+        def frame(count=None):
+            color.clear(0)
+            depth.clear(1.0)
+            shadow.clear(1.0)
+            p1.render(geom, e.Empty(), shadow)
+            if count is not None:
+                count.append(ctx.get_stats()["fragments"])
+            p2.render(geom, color, depth)
+
+        def frame_e2e():
+            geom.update(pv.data_ptr())
+            frame()
+            ctx._check(ctx._lib.euc_buf_download(ctx._p, color.handle, host_out.data_ptr(), h * w * 4))
+
+        h2d, d2h = pv.numel(), h * w * 4
+        config_extra = {"partition": "replicas" if world > 1 else "single GPU", "l2": "flush: 256 MB scratch write between timed frames" if wl == "c1" else "targets 100 MB + records; no flush"}
+    elif wl == "c2":
+        geom = e.Geometry(scene["verts"], scene["idx"], ctx)
+        tex = e.Buffer2d.from_array(scene["tex"], ctx)
+        color = e.Buffer2d([w, h], np.uint32, ctx)
+        pipe = e.Cube(scene["mvp"], tex.linear().tiled())
+        host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
+        pv = torch.from_numpy(scene["verts"].view(np.uint8)).pin_memory()
+        pi = torch.from_numpy(scene["idx"].view(np.uint8)).pin_memory()
+        keep += [pv, pi, host_out]
+
+        def frame():
+            color.clear(180)
+            pipe.render(geom, color, e.Empty())
+
+        def frame_e2e():
+            geom.update(pv.data_ptr(), pi.data_ptr())
+            frame()
+            ctx._check(ctx._lib.euc_buf_download(ctx._p, color.handle, host_out.data_ptr(), h * w * 4))
+
+        h2d, d2h = pv.numel() + pi.numel(), h * w * 4
+        config_extra = {"partition": "replicas" if world > 1 else "single GPU", "l2": "flush: 256 MB scratch write between timed frames"}
+    elif wl == "c5":
+        n = scene["n_icons"]
+        geom = e.Geometry(scene["verts"], scene["idx"], ctx)
+        color = e.Buffer2d([w, h], np.uint32, ctx, layers=n)
+        depth = e.Buffer2d([w, h], np.float32, ctx, layers=n)
+        pipe = e.VoxelIcon(np.eye(4), e.scenes.VOXEL_LIGHT_DIR)
+        pv = torch.from_numpy(scene["verts"].view(np.uint8)).pin_memory()
+        pi = torch.from_numpy(scene["idx"].view(np.uint8)).pin_memory()
+        host_out = torch.empty(n * h * w, dtype=torch.int32).pin_memory()
+        keep += [pv, pi, host_out]
+
+        def frame():
+            color.clear(0)
+            depth.clear(1.0)
+            pipe.render_batch(geom, scene["draws"], scene["ubs"], color, depth)
+
+        def frame_e2e():
+            geom.update(pv.data_ptr(), pi.data_ptr())
+            frame()
+            ctx._check(ctx._lib.euc_buf_download(ctx._p, color.handle, host_out.data_ptr(), n * h * w * 4))
+
+        h2d, d2h = pv.numel() + pi.numel(), n * h * w * 4
+        config_extra = {"partition": f"{n} icons per rank x {world} rank(s), no collective", "icons_per_step": n * world,
+                        "l2": f"targets {n * w * h * 8 / 1e6:.0f} MB > 126 MB L2; no flush"}
+
+    flush_buf = torch.empty(64 * 1024 * 1024, dtype=torch.int32, device="cuda") if wl in ("c1", "c2") else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k, flush):
+        """k steps on the device clock: events bracket each step (so an L2 flush between steps is excluded)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        if flush is None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(k):
+                fn()
+            b.record(stream)
+            barrier()
+            ms = a.elapsed_time(b)
+        else:
+            for a, b in evs:
+                flush.fill_(1)
+                a.record(stream)
+                fn()
+                b.record(stream)
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # fragment count of one frame (the reference's emit_fragment count), outside the timed region
+    ctx.set_stats(True)
+    first_pass = []
+    if wl in ("c1", "c3"):
+        frame(first_pass)  # two passes: stats are per render call
+    else:
+        frame()
+    st = ctx.get_stats()
+    ctx.set_stats(False)
+    frags_per_frame = int(st["fragments"]) + sum(first_pass)
+    tf = torch.tensor([frags_per_frame], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tf)  # bands / icon shards add up
+    frags_per_frame = int(tf.item())
+
+    for _ in range(warm):
+        frame()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.get_profile(reset=True)
+    ctx.set_profiling(True)
+    l0 = ctx.launch_count()
+    ms = timed(frame, steps, flush_buf)
+    launches = ctx.launch_count() - l0
+    prof = ctx.get_profile(reset=True)
+    ctx.set_profiling(False)
+    # e2e
+    for _ in range(2):
+        frame_e2e()
+    e2e_steps = max(3, min(steps, 50))
+    ms_e2e = timed(frame_e2e, e2e_steps, flush_buf)
+    clocks = sampler.result()
+
+    frames_per_step = 1 if wl != "c5" else scene["n_icons"] * world
+    job_mult = 1 if wl in ("c4", "c5") else world  # replicas render independent frames
+    value = frames_per_step * job_mult * steps / (ms / 1000.0)
+    e2e_value = frames_per_step * job_mult * e2e_steps / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+        raster_ms, raster_calls = prof["raster"]
+        alg = algorithmic_bytes(wl, args, scene)
+        if wl in ("c1", "c3"):
+            per_launch_bytes = alg / 2.0  # two raster launches (shadow, phong) share the frame's bytes
+        else:
+            per_launch_bytes = alg / (world if wl == "c4" else 1)
+        avg_raster_s = (raster_ms / max(raster_calls, 1)) / 1000.0
+        achieved = per_launch_bytes / avg_raster_s / 1e9 if avg_raster_s > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(wl)
+        stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+        line = {
+            "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak" if wl == "c5" else ("strong" if wl == "c4" else "weak"),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict({"workload": c["name"], "target": f"{w}x{h}", "frames_per_step": frames_per_step}, **config_extra),
+            "mfrag_per_s": frags_per_frame * job_mult * steps / (ms / 1000.0) / 1e6,
+            "fragments_per_step": frags_per_frame,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_raster_s * 1000.0,
+                         "peak_source": peak_src, "frame_frac": (alg / ((ms / steps) / 1000.0) / 1e9) / peak if wl != "c5" else None},
+            "stage_ms_per_launch": stage_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                run, scale, desc, cores = cpu_plan(wl, scene)
+                run()
+                t_cpu = min(run() for _ in range(2)) * scale
+                line["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc + "; best of 2 after 1 warm-up"}
+            except Exception as ex:  # the oracle is a reported baseline, never a dependency of the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ HAND_LEFT, HAND_RIGHT = range(2)
 FILTER_NEAREST, FILTER_LINEAR = range(2)
 WRAP_NONE, WRAP_CLAMP, WRAP_TILE, WRAP_MIRROR = range(4)
 TEXEL_F32, TEXEL_RGBA8_TO_F32 = range(2)
+STAGE_NAMES = ("setup", "alloc", "fill", "sort", "raster")
 
 
 class SamplerDesc(C.Structure):
@@ -63,7 +64,12 @@ SYMBOLS = {
     "euc_buf_download": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_buf_device_ptr": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "euc_buf_size": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "euc_buf_wrap": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "euc_set_profiling": (C.c_int, [_ctx_p, C.c_int]),
+    "euc_get_profile": (C.c_int, [_ctx_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_int]),
+    "euc_launch_count": (C.c_uint64, [_ctx_p]),
     "euc_geom_create": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "euc_geom_update": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "euc_geom_destroy": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_render": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
     "euc_render_geom": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64]),

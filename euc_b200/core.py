@@ -138,6 +138,19 @@ class Context:
         self._check(self._lib.euc_get_stats(self._p, C.byref(s)))
         return {"primitives": s.primitives, "binned_pairs": s.binned_pairs, "fragments": s.fragments}
 
+    def set_profiling(self, enabled):
+        self._check(self._lib.euc_set_profiling(self._p, 1 if enabled else 0))
+
+    def get_profile(self, reset=True):
+        """{stage: (milliseconds, launches)} accumulated since the last reset (blocking)."""
+        n = len(abi.STAGE_NAMES)
+        ms, calls = (C.c_float * n)(), (C.c_uint64 * n)()
+        self._check(self._lib.euc_get_profile(self._p, ms, calls, 1 if reset else 0))
+        return {abi.STAGE_NAMES[i]: (float(ms[i]), int(calls[i])) for i in range(n)}
+
+    def launch_count(self):
+        return int(self._lib.euc_launch_count(self._p))
+
     def close(self):
         if getattr(self, "_p", None):
             self._lib.euc_shutdown(self._p)
@@ -182,15 +195,23 @@ class Buffer2d:
     """Device-resident Buffer2d<T> with 4-byte texels (u32 colour, f32 depth, RGBA8 texture), row-major x + w*y.
     `layers` > 1 makes an array of equally sized targets (batch rendering)."""
 
-    def __init__(self, size, dtype, ctx=None, layers=1):
+    def __init__(self, size, dtype, ctx=None, layers=1, wrap_ptr=None):
         self.ctx = ctx or default_context()
         self.dtype = np.dtype(dtype)
         assert self.dtype.itemsize == 4
         self._size = [int(size[0]), int(size[1])]
         self.layers = int(layers)
         h = C.c_uint64()
-        self.ctx._check(self.ctx._lib.euc_buf_create(self.ctx._p, self._size[0], self._size[1], self.layers, 4, C.byref(h)))
+        if wrap_ptr is None:
+            self.ctx._check(self.ctx._lib.euc_buf_create(self.ctx._p, self._size[0], self._size[1], self.layers, 4, C.byref(h)))
+        else:  # caller-owned device memory (e.g. a torch tensor's storage); the caller keeps it alive
+            self.ctx._check(self.ctx._lib.euc_buf_wrap(self.ctx._p, C.c_void_p(int(wrap_ptr)), self._size[0], self._size[1],
+                                                       self.layers, 4, C.byref(h)))
         self.handle = h.value
+
+    @classmethod
+    def wrap(cls, device_ptr, size, dtype, ctx=None, layers=1):
+        return cls(size, dtype, ctx, layers, wrap_ptr=device_ptr)
 
     @classmethod
     def fill(cls, size, item, dtype=None, ctx=None, layers=1):
@@ -277,6 +298,11 @@ class Geometry:
             self.ctx._p, v.ctypes.data_as(C.c_void_p), self.stride, self.n_vertices,
             idx.ctypes.data_as(C.c_void_p) if idx is not None else None, self.n_indices, C.byref(h)))
         self.handle = h.value
+
+    def update(self, vertices_ptr, indices_ptr=None):
+        """Re-upload from host memory (raw addresses, e.g. of pinned buffers); asynchronous on the context's stream."""
+        self.ctx._check(self.ctx._lib.euc_geom_update(self.ctx._p, self.handle, C.c_void_p(vertices_ptr),
+                                                      C.c_void_p(indices_ptr) if indices_ptr else None))
 
     def destroy(self):
         if self.handle:

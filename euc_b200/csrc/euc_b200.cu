@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <array>
 #include <vector>
 
 using namespace eucb;
@@ -20,6 +21,7 @@ struct Buf {
     void* d = nullptr;
     uint32_t w = 0, h = 0, layers = 0, texel = 0;
     size_t bytes = 0;
+    bool owned = true;
 };
 struct Geom {
     uint8_t* verts = nullptr;
@@ -47,6 +49,13 @@ struct euc_ctx {
     bool stats = false;
     euc_render_stats last{};
     int sm_count = 148;
+    uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[EUC_STAGE_COUNT + 1] = {};
+    std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
+    std::vector<cudaEvent_t> ev_pool;
+    float prof_ms[EUC_STAGE_COUNT] = {};
+    uint64_t prof_calls[EUC_STAGE_COUNT] = {};
 };
 
 namespace {
@@ -81,6 +90,34 @@ int ensure(euc_ctx* ctx, Scratch& s, size_t bytes, bool zero_new = false) {
     s.cap = cap;
     if (zero_new) CU(cudaMemsetAsync(s.p, 0, cap, ctx->stream));
     return EUC_OK;
+}
+
+cudaEvent_t get_event(euc_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {  // brackets one kernel launch with events when profiling is on
+    euc_ctx* ctx; int stage; cudaEvent_t a = nullptr;
+    StageTimer(euc_ctx* c, int s) : ctx(c), stage(s) {
+        ++ctx->launches;
+        if (ctx->profiling) { a = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    ~StageTimer() {
+        if (a) { cudaEvent_t b = get_event(ctx); cudaEventRecord(b, ctx->stream); ctx->pending[stage].push_back({a, b}); }
+    }
+};
+void drain_profile(euc_ctx* ctx) {  // stream must be synchronised
+    for (int s = 0; s < EUC_STAGE_COUNT; ++s) {
+        for (auto& pr : ctx->pending[s]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr[0], pr[1]) == cudaSuccess) { ctx->prof_ms[s] += ms; ctx->prof_calls[s] += 1; }
+            ctx->ev_pool.push_back(pr[0]);
+            ctx->ev_pool.push_back(pr[1]);
+        }
+        ctx->pending[s].clear();
+    }
 }
 
 template <class P> struct PipeInfo {
@@ -120,8 +157,8 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
 
     CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
-    setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm);
-    alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles);
+    { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+    { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
     CU(cudaGetLastError());
     // The pair count sizes the list; it is also where out-of-range indices are reported (reference: slice panic).
     CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -141,13 +178,16 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     prm.tile_list = (uint32_t*)ctx->tile_list.p;
     prm.list_capacity = (uint32_t)(ctx->tile_list.cap / 4);
 
-    fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm);
-    sort_lists_kernel<<<(n_tiles + 3) / 4, 128, 0, ctx->stream>>>(prm, n_tiles);
+    { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+    { StageTimer t(ctx, EUC_STAGE_SORT); sort_lists_kernel<<<(n_tiles + 3) / 4, 128, 0, ctx->stream>>>(prm, n_tiles); }
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
-    if (prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write)
-        raster_kernel<P, true><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
-    else
-        raster_kernel<P, false><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+    {
+        StageTimer t(ctx, EUC_STAGE_RASTER);
+        if (prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write)
+            raster_kernel<P, true><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+        else
+            raster_kernel<P, false><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+    }
     CU(cudaGetLastError());
     return EUC_OK;
 }
@@ -328,7 +368,9 @@ int euc_shutdown(euc_ctx* ctx) {
     if (!ctx) return EUC_E_INVALID;
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->bufs) cudaFree(kv.second.d);
+    for (auto& kv : ctx->bufs) if (kv.second.owned) cudaFree(kv.second.d);
+    drain_profile(ctx);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx};
     for (Scratch* s : ss) cudaFree(s->p);
@@ -385,12 +427,45 @@ int euc_buf_create(euc_ctx* ctx, uint32_t width, uint32_t height, uint32_t layer
     return EUC_OK;
 }
 
+int euc_buf_wrap(euc_ctx* ctx, void* device_ptr, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out) {
+    if (!ctx || !out || !device_ptr) return EUC_E_INVALID;
+    if (texel_bytes != 4 || layers == 0) return fail(ctx, EUC_E_UNSUPPORTED, "only 4-byte texels, layers >= 1");
+    if (((uintptr_t)device_ptr & 15u) != 0) return fail(ctx, EUC_E_INVALID, "wrapped device memory must be 16-byte aligned");
+    Buf b;
+    b.d = device_ptr; b.w = width; b.h = height; b.layers = layers; b.texel = texel_bytes; b.owned = false;
+    b.bytes = (size_t)width * height * layers * texel_bytes;
+    uint64_t hnd = ctx->next_handle++;
+    ctx->bufs[hnd] = b;
+    *out = hnd;
+    return EUC_OK;
+}
+
+int euc_set_profiling(euc_ctx* ctx, int enabled) {
+    if (!ctx) return EUC_E_INVALID;
+    ctx->profiling = enabled != 0;
+    return EUC_OK;
+}
+
+int euc_get_profile(euc_ctx* ctx, float* ms, uint64_t* calls, int reset) {
+    if (!ctx) return EUC_E_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    drain_profile(ctx);
+    for (int s = 0; s < EUC_STAGE_COUNT; ++s) {
+        if (ms) ms[s] = ctx->prof_ms[s];
+        if (calls) calls[s] = ctx->prof_calls[s];
+        if (reset) { ctx->prof_ms[s] = 0.f; ctx->prof_calls[s] = 0; }
+    }
+    return EUC_OK;
+}
+
+uint64_t euc_launch_count(euc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
 int euc_buf_destroy(euc_ctx* ctx, euc_buf buf) {
     if (!ctx) return EUC_E_INVALID;
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     CU(cudaStreamSynchronize(ctx->stream));
-    if (it->second.d) CU(cudaFree(it->second.d));
+    if (it->second.d && it->second.owned) CU(cudaFree(it->second.d));
     ctx->bufs.erase(it);
     return EUC_OK;
 }
@@ -406,6 +481,7 @@ int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel) {
     std::memcpy(&v, texel, 4);
     const size_t vec = (n + 3) / 4;
     const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
+    ++ctx->launches;
     fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)b.d, n, v);
     CU(cudaGetLastError());
     return EUC_OK;
@@ -466,6 +542,19 @@ int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, 
     uint64_t hnd = ctx->next_handle++;
     ctx->geoms[hnd] = g;
     *out = hnd;
+    return EUC_OK;
+}
+
+int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uint32_t* indices) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    Geom& g = it->second;
+    if (vertices && g.n_verts) CU(cudaMemcpyAsync(g.verts, vertices, (size_t)g.stride * g.n_verts, cudaMemcpyHostToDevice, ctx->stream));
+    if (indices) {
+        if (!g.idx) return fail(ctx, EUC_E_INVALID, "geometry has no index buffer");
+        if (g.n_idx) CU(cudaMemcpyAsync(g.idx, indices, (size_t)g.n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return EUC_OK;
 }
 

@@ -172,6 +172,13 @@ int euc_sync(euc_ctx* ctx);
 /* Enable (1) / disable (0) fragment counting; counting costs one atomic per warp per tile. */
 int euc_set_stats(euc_ctx* ctx, int enabled);
 int euc_get_stats(euc_ctx* ctx, euc_render_stats* out); /* blocking; stats of the last render call */
+/* Per-stage device timing (CUDA events on the context's stream around every kernel of a render call). */
+enum euc_stage { EUC_STAGE_SETUP = 0, EUC_STAGE_ALLOC = 1, EUC_STAGE_FILL = 2, EUC_STAGE_SORT = 3, EUC_STAGE_RASTER = 4, EUC_STAGE_COUNT = 5 };
+int euc_set_profiling(euc_ctx* ctx, int enabled);
+/* Blocking. ms[EUC_STAGE_COUNT] = accumulated milliseconds per stage since the last reset; calls[] = launches per stage. */
+int euc_get_profile(euc_ctx* ctx, float* ms, uint64_t* calls, int reset);
+/* Number of kernels this context has launched so far (clears included). */
+uint64_t euc_launch_count(euc_ctx* ctx);
 
 /* ---- Buffer2d --------------------------------------------------------------------------------------- */
 /* `layers` > 1 creates an array of equally sized targets stored back to back (batch rendering). texel_bytes: 4. */
@@ -182,12 +189,16 @@ int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes);  
 int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes);           /* blocking */
 int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes);
 int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* layers);
+/* Wrap caller-owned device memory (e.g. a slice of a collective's receive buffer) as a Buffer2d. Not freed by destroy. */
+int euc_buf_wrap(euc_ctx* ctx, void* device_ptr, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out);
 
 /* ---- geometry --------------------------------------------------------------------------------------- */
 /* indices may be NULL (non-indexed stream). Indices are u32 on the device (the reference uses usize). */
 int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices,
                     const uint32_t* indices, uint32_t n_indices, euc_geom* out);
 int euc_geom_destroy(euc_ctx* ctx, euc_geom geom);
+/* Re-upload vertices (and indices) into an existing geom of the same shape; asynchronous when the host memory is pinned. */
+int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uint32_t* indices);
 
 /* ---- render ----------------------------------------------------------------------------------------- */
 /* Pipeline::render with host geometry: uploads, renders, returns without waiting for the device. */
