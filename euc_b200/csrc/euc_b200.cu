@@ -182,11 +182,17 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     { StageTimer t(ctx, EUC_STAGE_SORT); sort_lists_kernel<<<(n_tiles + 3) / 4, 128, 0, ctx->stream>>>(prm, n_tiles); }
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
     {
+        constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
+        const size_t smem = raster_smem_bytes<P>();
+        const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
+        auto kern = msaa ? raster_kernel<P, true, DEFER> : raster_kernel<P, false, DEFER>;
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[msaa]) {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[msaa] = true;
+        }
         StageTimer t(ctx, EUC_STAGE_RASTER);
-        if (prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write)
-            raster_kernel<P, true><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
-        else
-            raster_kernel<P, false><<<rblocks, RASTER_WARPS * 32, 0, ctx->stream>>>(prm, n_tiles);
+        kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles);
     }
     CU(cudaGetLastError());
     return EUC_OK;

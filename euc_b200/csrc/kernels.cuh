@@ -40,6 +40,7 @@ enum : int {
     R_BBY = 19,  // y0 | y1 << 16     (bounds clamped to [0, h]; per-band clamp happens per row)
     R_FLAGS = 20,  // bit0: all three vertices pass the z clip
     R_DRAW = 21,
+    R_TRI = 22,  // primitive index inside this render call
     R_VAR = 24
 };
 
@@ -282,7 +283,7 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
             auto pick = [&](const float* a, int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]); };
             r4[3] = make_float4(pick(sxs, o0), pick(sys, o0), pick(sxs, o1), pick(sys, o1));
             r4[4] = make_float4(pick(sxs, o2), pick(sys, o2), __uint_as_float(bbox.x), __uint_as_float(bbox.y));
-            r4[5] = make_float4(__uint_as_float(nvc ? 1u : 0u), __uint_as_float(d), 0.0f, 0.0f);
+            r4[5] = make_float4(__uint_as_float(nvc ? 1u : 0u), __uint_as_float(d), __uint_as_float(tri), 0.0f);
             if constexpr (P::V > 0) {
                 float flat[L::VPAD];
 #pragma unroll
@@ -438,14 +439,54 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 // -------------------------------------------------------------------------------------------------------
 // K4 / K5: tile raster.
+//
+// One warp per 16x16 tile, lane = (row, half) -> 8 consecutive pixels whose depth and colour stay in registers for
+// the whole tile list.  Setup records arrive in shared memory in batches of BATCH through cp.async.bulk (one bulk
+// copy per record, issued by BATCH different lanes, completion on an mbarrier; two stages).
+//
+// Lanes do NOT walk the batch in lock-step: lane t first computes which lanes triangle t's bounds touch, the 32x32
+// bit matrix is transposed with ballots, and every lane then iterates only over the triangles that overlap its own
+// segment (its own cursor, submission order preserved per lane — which is all euc's ordering semantics need, because
+// different lanes own disjoint pixels).  This is what keeps warp execution efficiency up for small triangles.
+//
+// DEFER (pipelines whose blend ignores the old pixel and whose fragment stage is pure): the loop only resolves, per
+// pixel, the LAST triangle whose fragment passed the depth test; fragment + blend run once per pixel afterwards.
+// With any depth mode that is the reference's final pixel: blend(_, fragment(last passing)) (pipeline.rs:574-576).
 // -------------------------------------------------------------------------------------------------------
 constexpr int RASTER_WARPS = 4;
-constexpr int BATCH = 8;  // setup records per bulk-copy stage
+constexpr int BATCH = 32;  // setup records per bulk-copy stage (== warp size: one lane-mask per lane)
+constexpr uint32_t NO_WINNER = 0xffffffffu;
 
-template <class P> struct RasterSmem {
-    alignas(128) uint32_t rec[RASTER_WARPS][2][BATCH][RecLayout<P>::WORDS];
-    alignas(8) uint64_t bar[RASTER_WARPS][2];
-};
+// Immediate-mode pipelines (blend reads the old pixel) queue passing fragments per lane and shade them with all
+// lanes in lock-step: entry = triangle-in-batch << 8 | 8-bit mask of this lane's pixels that passed.
+constexpr int Q_ENTRIES = 12;     // entries per lane (u16), lane stride 7 words -> conflict-free banks
+constexpr int Q_STRIDE_WORDS = 7;
+constexpr int Q_FRAGS = 20;       // stop generating once a lane holds this many fragments
+constexpr int COL_STRIDE = 9;     // colour row of a lane: 8 words + 1 pad
+
+template <class P> constexpr size_t raster_smem_bytes() {
+    return (size_t)RASTER_WARPS * (2 * BATCH * RecLayout<P>::BYTES + 16 + 32 * (Q_STRIDE_WORDS + COL_STRIDE) * 4);
+}
+
+// interpolate() reading the setup record from shared memory with 128-bit loads (lanes address different records)
+template <class P> __device__ __forceinline__ void interpolate_smem(const float4* __restrict__ rec4, float xf, float yf, float* var) {
+    const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
+    const float wh0 = (q0.x + q1.z * yf) + q0.w * xf;
+    const float wh1 = (q0.y + q1.w * yf) + q1.x * xf;
+    const float wh2 = (q0.z + q2.x * yf) + q1.y * xf;
+    const float wu2 = wh2 - wh0 - wh1;
+    const float r = 1.0f / wh2;
+    const float w0 = wh0 * r, w1 = wh1 * r, w2 = wu2 * r;
+    constexpr int NV4 = RecLayout<P>::VPAD / 4;
+    float vv[NV4 * 4 > 0 ? NV4 * 4 : 1];
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        const float4 t = rec4[R_VAR / 4 + k];
+        vv[4 * k] = t.x; vv[4 * k + 1] = t.y; vv[4 * k + 2] = t.z; vv[4 * k + 3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < P::V; ++k) var[k] = vv[k] * w0 + vv[P::V + k] * w1 + vv[2 * P::V + k] * w2;
+}
 
 // get_v_data (triangles.rs:274-294): closed-form weights at (x, y), perspective divide, weighted_sum3 (math.rs:38-40)
 template <class P> __device__ __forceinline__ void interpolate(const float* __restrict__ rec, float xf, float yf, float* var) {
@@ -469,13 +510,60 @@ __device__ __forceinline__ void shade_at(const typename P::Uniforms& u, const Sa
     P::fragment(u, samp, var, frag);
 }
 
-template <class P, bool MSAA> __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
-    using L = RecLayout<P>;
-    __shared__ RasterSmem<P> sm;
+// euc's coarse-shading "MSAA" (pipeline.rs:544-570) for one pixel; corner fragments are memoised in the reference
+// (pure function of corner and primitive), so recomputing them is exact.  `cache` carries the corner pair of the
+// previous pixel group: cx0 of this group may equal cx1 of the previous one.
+struct CornerCache {
+    uint32_t tri, cx, cy0;  // owner triangle, corner x, corner-row base of the cached column
+    float t0[4], t1[4];     // fragments at (cx, cy0) and (cx, cy1)
+};
+template <class P>
+__device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, const SamplerDev* samp, const float* rec, uint32_t tri, uint32_t x,
+                                               uint32_t y, uint32_t band_lo, uint32_t Lv, CornerCache& left, CornerCache& right, float* frag) {
+    const float msaa_div = 1.0f / (float)(1u << Lv);
+    const uint32_t rx = x, ry = y - band_lo;  // x - tgt_min[0], y - tgt_min[1]
+    const float fractx = r_fract((float)rx * msaa_div), fracty = r_fract((float)ry * msaa_div);
+    const uint32_t posix = rx >> Lv, posiy = ry >> Lv;
+    const uint32_t cx0 = (posix + 0u) << Lv, cx1 = (posix + 1u) << Lv;
+    const uint32_t cy0 = band_lo + ((posiy + 0u) << Lv), cy1 = band_lo + ((posiy + 1u) << Lv);
+    if (!(left.tri == tri && left.cx == cx0 && left.cy0 == cy0)) {
+        if (right.tri == tri && right.cx == cx0 && right.cy0 == cy0) {
+            left = right;
+        } else {
+            shade_at<P>(u, samp, rec, (float)cx0, (float)cy0, left.t0);
+            shade_at<P>(u, samp, rec, (float)cx0, (float)cy1, left.t1);
+            left.tri = tri; left.cx = cx0; left.cy0 = cy0;
+        }
+    }
+    if (!(right.tri == tri && right.cx == cx1 && right.cy0 == cy0)) {
+        shade_at<P>(u, samp, rec, (float)cx1, (float)cy0, right.t0);
+        shade_at<P>(u, samp, rec, (float)cx1, (float)cy1, right.t1);
+        right.tri = tri; right.cx = cx1; right.cy0 = cy0;
+    }
+    const float omy = 1.0f - fracty, omx = 1.0f - fractx;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float t0 = left.t0[c] * omy + left.t1[c] * fracty;    // weighted_sum2(t00, t01, 1-fy, fy)
+        const float t1 = right.t0[c] * omy + right.t1[c] * fracty;  // weighted_sum2(t10, t11, 1-fy, fy)
+        frag[c] = t0 * omx + t1 * fractx;                           // weighted_sum2(t0, t1, 1-fx, fx)
+    }
+}
 
+template <class P, bool MSAA, bool DEFER>
+__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+    using L = RecLayout<P>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    constexpr uint32_t STAGE_WORDS = BATCH * L::WORDS;
+    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * 2 * STAGE_WORDS;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * 2 * STAGE_WORDS * 4) + warp * 2;
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (2 * STAGE_WORDS * 4 + 16)) +
+                              warp * 32 * (Q_STRIDE_WORDS + COL_STRIDE);
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
+    uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
+    constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
+
     const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
-    uint64_t* bar = sm.bar[warp];
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -490,165 +578,242 @@ template <class P, bool MSAA> __global__ void __launch_bounds__(RASTER_WARPS * 3
     const uint32_t layer = tile / tiles_per_layer;
     const uint32_t tl = tile - layer * tiles_per_layer;
     const uint32_t ty = tl / p.tiles_x, tx = tl - ty * p.tiles_x;
-    const uint32_t y = ty * TILE + (lane >> 1);
-    const uint32_t segx0 = tx * TILE + (lane & 1u) * 8u;
-    const bool row_ok = y < p.h && y >= p.row_begin && y < p.row_end;
+    const uint32_t tile_x0 = tx * TILE, tile_y0 = ty * TILE;
+    const uint32_t y = tile_y0 + (lane >> 1);
+    const uint32_t segx0 = tile_x0 + (lane & 1u) * 8u;
+    const bool row_ok = y < p.h && y >= p.row_begin && y < p.row_end && segx0 < p.w;
     const float yf = (float)y;
-    // euc band of this row (pipeline.rs:341-349): tgt_min.y = lo, tgt_max.y = hi
+    // euc band of this row (pipeline.rs:341-349): tgt_min.y = band_lo, tgt_max.y = band_hi
     const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
     const uint32_t band_hi = min(band_lo + p.group_rows, p.h);
 
     const size_t layer_off = (size_t)layer * p.w * p.h;
+    const size_t base = layer_off + (size_t)y * p.w + segx0;
+    const bool vec_ok = segx0 + 8u <= p.w && (p.w & 3u) == 0;
+    const bool shade_px = P::HAS_FRAGMENT && p.pixel_write;
     float depth[8];
-    uint32_t color[8];
-    const bool full_seg = segx0 + 8u <= p.w;
-    {
-        const size_t base = layer_off + (size_t)y * p.w + segx0;
+    uint32_t cw[8];  // colour (immediate mode) or winning triangle id (deferred mode)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { depth[j] = 0.0f; color[j] = 0u; }
-        if (row_ok && p.uses_depth) {
-            if (full_seg && (p.w & 3u) == 0) {
-                float4 a = *reinterpret_cast<const float4*>(p.depth + base), b = *reinterpret_cast<const float4*>(p.depth + base + 4);
-                depth[0] = a.x; depth[1] = a.y; depth[2] = a.z; depth[3] = a.w; depth[4] = b.x; depth[5] = b.y; depth[6] = b.z; depth[7] = b.w;
-            } else {
+    for (int j = 0; j < 8; ++j) { depth[j] = 0.0f; cw[j] = DEFER ? NO_WINNER : 0u; }
+    if (row_ok && p.uses_depth) {
+        if (vec_ok) {
+            const float4 a = *reinterpret_cast<const float4*>(p.depth + base), b = *reinterpret_cast<const float4*>(p.depth + base + 4);
+            depth[0] = a.x; depth[1] = a.y; depth[2] = a.z; depth[3] = a.w; depth[4] = b.x; depth[5] = b.y; depth[6] = b.z; depth[7] = b.w;
+        } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) depth[j] = p.depth[base + j];
-            }
+            for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) depth[j] = p.depth[base + j];
         }
-        if (row_ok && p.pixel_write) {
-            if (full_seg && (p.w & 3u) == 0) {
-                uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
-                color[0] = a.x; color[1] = a.y; color[2] = a.z; color[3] = a.w; color[4] = b.x; color[5] = b.y; color[6] = b.z; color[7] = b.w;
-            } else {
+    }
+    if (QUEUE && row_ok && shade_px) {
+        if (vec_ok) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
+            cw[0] = a.x; cw[1] = a.y; cw[2] = a.z; cw[3] = a.w; cw[4] = b.x; cw[5] = b.y; cw[6] = b.z; cw[7] = b.w;
+        } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) color[j] = p.pixel[base + j];
-            }
+            for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) cw[j] = p.pixel[base + j];
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) col_sm[j] = cw[j];
     }
 
     uint32_t nfrag = 0;
     const uint32_t n_batches = (n + BATCH - 1) / BATCH;
-    // stage 0: issue batch 0
-    auto issue = [&](uint32_t b, uint32_t id) {
-        // lanes [0, cnt) each copy one record of batch b; id = triangle index held by this lane
+    auto issue = [&](uint32_t b, uint32_t id) {  // lane i < cnt copies record i of batch b
         const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
         uint64_t* mb = &bar[b & 1u];
         if (lane == 0) mbar_expect_tx(mb, cnt * (uint32_t)L::BYTES);
         __syncwarp();
-        if (lane < cnt) bulk_g2s(sm.rec[warp][b & 1u][lane], p.recs + (size_t)id * L::WORDS, (uint32_t)L::BYTES, mb);
+        if (lane < cnt) bulk_g2s(recs_sm + (b & 1u) * STAGE_WORDS + lane * L::WORDS, p.recs + (size_t)id * L::WORDS, (uint32_t)L::BYTES, mb);
     };
-    uint32_t id_pf = lane < min((uint32_t)BATCH, n) ? __ldg(list + lane) : 0u;
+    uint32_t id_pf = lane < n ? __ldg(list + lane) : 0u;
     issue(0, id_pf);
-    id_pf = (BATCH + lane < n && lane < BATCH) ? __ldg(list + BATCH + lane) : 0u;
+    id_pf = (BATCH + lane < n) ? __ldg(list + BATCH + lane) : 0u;
 
     for (uint32_t b = 0; b < n_batches; ++b) {
-        // prefetch: records of batch b+1, ids of batch b+2
-        __syncwarp();  // all lanes finished reading stage (b+1)&1 in iteration b-1
+        __syncwarp();  // every lane is done with stage (b+1)&1 (read in iteration b-1)
         if (b + 1 < n_batches) {
             issue(b + 1, id_pf);
             const uint32_t pos = (b + 2) * BATCH + lane;
-            id_pf = (lane < BATCH && pos < n) ? __ldg(list + pos) : 0u;
+            id_pf = pos < n ? __ldg(list + pos) : 0u;
         }
         mbar_wait(&bar[b & 1u], (b >> 1) & 1u);
         const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
-        for (uint32_t t = 0; t < cnt; ++t) {
-            const uint32_t* recu = sm.rec[warp][b & 1u][t];
-            const float* rec = reinterpret_cast<const float*>(recu);
-            const uint32_t bbx = recu[R_BBX], bby = recu[R_BBY];
+        const uint32_t* stage = recs_sm + (b & 1u) * STAGE_WORDS;
+
+        // lane t: which lanes (row, half) does triangle t's bounding box touch?
+        uint32_t m = 0;
+        if (lane < cnt) {
+            const uint32_t bbx = stage[lane * L::WORDS + R_BBX], bby = stage[lane * L::WORDS + R_BBY];
             const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
-            // lane-level reject: row outside bbox, segment outside bbox
-            if (!row_ok || y < y0 || y >= y1 || segx0 >= x1 || segx0 + 8u <= x0) continue;
-            // band-clamped vertical bounds (triangles.rs:114-139 with tgt_min/max of this row's band)
-            const uint32_t bymin = min(max(y0, band_lo), band_hi), bymax = min(max(y1, band_lo), band_hi);
-            const uint32_t extent = (x1 - x0) * (bymax - bymin);
-            uint32_t r0, r1;
-            if (extent < 128u) {  // :224-226
-                r0 = x0; r1 = x1;
-            } else {  // :228-253
-                const float a_x = rec[R_VY + 0], a_y = rec[R_VY + 1], b_x = rec[R_VY + 2], b_y = rec[R_VY + 3], c_x = rec[R_VY + 4], c_y = rec[R_VY + 5];
-                const float ac = a_x + ((yf - a_y) / (c_y - a_y)) * (c_x - a_x);
-                float lo, hi;
-                if (yf < b_y) {
-                    const float ab = a_x + ((yf - a_y) / (b_y - a_y)) * (b_x - a_x);
-                    lo = r_min(ab, ac); hi = r_max(ab, ac);
-                } else {
-                    const float bc = b_x + ((yf - b_y) / (c_y - b_y)) * (c_x - b_x);
-                    lo = r_min(bc, ac); hi = r_max(bc, ac);
-                }
-                const float e0 = floorf(lo), e1 = ceilf(hi);
-                const float fx0 = (float)x0, fx1 = (float)x1;
-                r0 = (e0 >= fx0 && e0 < fx1) ? __float2uint_rz(e0) : x0;
-                r1 = (e1 >= fx0 && e1 < fx1) ? __float2uint_rz(e1) : x1;
+            const uint32_t ra = max(y0, tile_y0) - tile_y0, rb = min(y1, tile_y0 + TILE) - tile_y0;  // rows [ra, rb) of the tile
+            if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra) {
+                const uint32_t hi = rb >= 16u ? 0xffffffffu : ((1u << (2u * rb)) - 1u);
+                const uint32_t lo = (1u << (2u * ra)) - 1u;
+                uint32_t seg = 0;
+                if (x0 < tile_x0 + 8u && x1 > tile_x0) seg |= 0x55555555u;
+                if (x0 < tile_x0 + 16u && x1 > tile_x0 + 8u) seg |= 0xaaaaaaaau;
+                m = hi & ~lo & seg;
             }
-            if (segx0 >= r1 || segx0 + 8u <= r0 || r1 <= r0) continue;
-            // chain start (:257-260) and replay up to this lane's segment (:301)
-            const float dx0 = rec[R_DX + 0], dx1 = rec[R_DX + 1], dx2 = rec[R_DX + 2];
-            const float r0f = (float)r0;
-            float w0 = (rec[R_O + 0] + rec[R_DY + 0] * yf) + dx0 * r0f;
-            float w1 = (rec[R_O + 1] + rec[R_DY + 1] * yf) + dx1 * r0f;
-            float w2 = (rec[R_O + 2] + rec[R_DY + 2] * yf) + dx2 * r0f;
-            if (segx0 > r0) {
-                const uint32_t npre = segx0 - r0;
-#pragma unroll 4
-                for (uint32_t i = 0; i < npre; ++i) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }
-            }
-            const float z0 = rec[R_ZH + 0], z1 = rec[R_ZH + 1], z2 = rec[R_ZH + 2];
-            const bool nvc = (recu[R_FLAGS] & 1u) != 0u;
-            const typename P::Uniforms& u = uniforms_of<P>(p, recu[R_DRAW]);
+        }
+        // transpose: own bit t <=> triangle t touches this lane
+        uint32_t own = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t x = segx0 + (uint32_t)j;
-                const bool inr = x >= r0 && x < r1;
-                const float wu2 = w2 - w0 - w1;                          // :264
-                if (inr && w0 >= 0.0f && w1 >= 0.0f && wu2 >= 0.0f) {    // :267
-                    const float z = z0 * w0 + z1 * w1 + z2 * wu2;        // :269
-                    bool pass = nvc || !p.zclip || (p.zmin <= z && z <= p.zmax);  // :271
-                    if (pass && p.depth_test != EUC_DEPTH_NONE) {        // pipeline.rs:519-526
-                        const float old_z = depth[j];
-                        pass = p.depth_test == EUC_DEPTH_LESS ? (z < old_z) : (p.depth_test == EUC_DEPTH_EQUAL ? (z == old_z) : (z > old_z));
+        for (int l = 0; l < 32; ++l) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> l) & 1u);
+            if ((int)lane == l) own = bits;
+        }
+        if (!row_ok) own = 0;
+
+        uint32_t qn = 0, qf = 0;  // queued entries / fragments of this lane
+        for (;;) {
+            // ---- generate: coverage + depth for this lane's own triangles, until its FIFO is nearly full ----
+            while (own && qn < (uint32_t)Q_ENTRIES && qf < (uint32_t)Q_FRAGS) {
+                const uint32_t t = (uint32_t)__ffs((int)own) - 1u;
+                own &= own - 1u;
+                const float4* rec4 = reinterpret_cast<const float4*>(stage + t * L::WORDS);
+                const float4 q4 = rec4[4];  // c.x c.y bbx bby
+                const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
+                const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
+                // band-clamped vertical bounds (triangles.rs:114-139 with tgt_min/max of this row's band)
+                const uint32_t bymin = min(max(y0, band_lo), band_hi), bymax = min(max(y1, band_lo), band_hi);
+                const uint32_t extent = (x1 - x0) * (bymax - bymin);
+                uint32_t r0, r1;
+                if (extent < 128u) {  // :224-226
+                    r0 = x0; r1 = x1;
+                } else {  // :228-253
+                    const float4 q3 = rec4[3];  // a.x a.y b.x b.y
+                    const float a_x = q3.x, a_y = q3.y, b_x = q3.z, b_y = q3.w, c_x = q4.x, c_y = q4.y;
+                    const float ac = a_x + ((yf - a_y) / (c_y - a_y)) * (c_x - a_x);
+                    float lo, hi;
+                    if (yf < b_y) {
+                        const float ab = a_x + ((yf - a_y) / (b_y - a_y)) * (b_x - a_x);
+                        lo = r_min(ab, ac); hi = r_max(ab, ac);
+                    } else {
+                        const float bc = b_x + ((yf - b_y) / (c_y - b_y)) * (c_x - b_x);
+                        lo = r_min(bc, ac); hi = r_max(bc, ac);
                     }
-                    if (pass) {
-                        ++nfrag;
-                        if (p.depth_write) depth[j] = z;                 // pipeline.rs:536-538
-                        if (P::HAS_FRAGMENT && p.pixel_write) {          // pipeline.rs:540-577
-                            float frag[4];
-                            if (!MSAA) {
-                                shade_at<P>(u, p.samp, rec, (float)x, yf, frag);
-                            } else {
-                                const uint32_t Lv = p.msaa_level;
-                                const float msaa_div = 1.0f / (float)(1u << Lv);
-                                const uint32_t rx = x, ry = y - band_lo;  // x - tgt_min[0], y - tgt_min[1]
-                                const float fractx = r_fract((float)rx * msaa_div), fracty = r_fract((float)ry * msaa_div);
-                                const uint32_t posix = rx >> Lv, posiy = ry >> Lv;
-                                const float cx0 = (float)((posix + 0u) << Lv), cx1 = (float)((posix + 1u) << Lv);
-                                const float cy0 = (float)(band_lo + ((posiy + 0u) << Lv)), cy1 = (float)(band_lo + ((posiy + 1u) << Lv));
-                                float t00[4], t10[4], t01[4], t11[4];
-                                shade_at<P>(u, p.samp, rec, cx0, cy0, t00);
-                                shade_at<P>(u, p.samp, rec, cx1, cy0, t10);
-                                shade_at<P>(u, p.samp, rec, cx0, cy1, t01);
-                                shade_at<P>(u, p.samp, rec, cx1, cy1, t11);
-                                const float omy = 1.0f - fracty, omx = 1.0f - fractx;
+                    const float e0 = floorf(lo), e1 = ceilf(hi);
+                    const float fx0 = (float)x0, fx1 = (float)x1;
+                    r0 = (e0 >= fx0 && e0 < fx1) ? __float2uint_rz(e0) : x0;
+                    r1 = (e1 >= fx0 && e1 < fx1) ? __float2uint_rz(e1) : x1;
+                }
+                if (!(segx0 >= r1 || segx0 + 8u <= r0 || r1 <= r0)) {
+                // pixels of this segment inside [r0, r1), and from which pixel on the chain advances (:262, :301)
+                const uint32_t jlo = r0 > segx0 ? r0 - segx0 : 0u, jhi = min(r1 - segx0, 8u);
+                const uint32_t inmask = ((1u << jhi) - 1u) & ~((1u << jlo) - 1u);
+                // chain start (:257-260) and replay up to this lane's segment (:301)
+                const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
+                const float dx0 = q0.w, dx1 = q1.x, dx2 = q1.y;
+                const float r0f = (float)r0;
+                float w0 = (q0.x + q1.z * yf) + dx0 * r0f;
+                float w1 = (q0.y + q1.w * yf) + dx1 * r0f;
+                float w2 = (q0.z + q2.x * yf) + dx2 * r0f;
+                if (segx0 > r0) {
+                    const uint32_t npre = segx0 - r0;
+#pragma unroll 4
+                    for (uint32_t i = 0; i < npre; ++i) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }
+                }
+                const float z0 = q2.y, z1 = q2.z, z2 = q2.w;
+                const float4 q5 = rec4[5];  // flags draw tri -
+                const bool zc = p.zclip && (__float_as_uint(q5.x) & 1u) == 0u;  // per-fragment z clip needed (:271)
+                const uint32_t tri_id = __float_as_uint(q5.z);
+                uint32_t passmask = 0;
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    const float t0 = t00[c] * omy + t01[c] * fracty;
-                                    const float t1 = t10[c] * omy + t11[c] * fracty;
-                                    frag[c] = t0 * omx + t1 * fractx;
-                                }
-                            }
-                            color[j] = P::blend(color[j], frag);
+                for (int j = 0; j < 8; ++j) {
+                    const float wu2 = w2 - w0 - w1;                                              // :264
+                    if (((inmask >> j) & 1u) && w0 >= 0.0f && w1 >= 0.0f && wu2 >= 0.0f) {      // :262, :267
+                        const float z = z0 * w0 + z1 * w1 + z2 * wu2;                            // :269
+                        bool pass = !zc || (p.zmin <= z && z <= p.zmax);
+                        if (p.depth_test != EUC_DEPTH_NONE) {                                    // pipeline.rs:519-526
+                            const float old_z = depth[j];
+                            pass = pass && (p.depth_test == EUC_DEPTH_LESS ? (z < old_z) : (p.depth_test == EUC_DEPTH_EQUAL ? (z == old_z) : (z > old_z)));
+                        }
+                        if (pass) {
+                            passmask |= 1u << j;
+                            if (p.depth_write) depth[j] = z;                                     // pipeline.rs:536-538
+                            if (DEFER) cw[j] = tri_id;
                         }
                     }
+                    if ((uint32_t)j >= jlo) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }     // :301
                 }
-                if (x >= r0) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }  // :301
+                nfrag += __popc(passmask);
+                if (QUEUE && passmask && shade_px) {
+                    queue[qn++] = (uint16_t)((t << 8) | passmask);
+                    qf += __popc(passmask);
+                }
+                }
             }
+            if (!QUEUE) break;  // the generate loop above ran to completion (its FIFO limits never trigger)
+            // ---- drain: fragment + blend (pipeline.rs:540-577) for the queued fragments, all lanes in lock-step ----
+            __syncwarp();  // reconverge: lanes leave the generate loop at different times
+            {
+                uint32_t k = 0, cur = 0, ct = 0;
+                for (;;) {
+                    if (cur == 0) {
+                        if (k == qn) break;
+                        const uint32_t e = queue[k++];
+                        cur = e & 0xffu;
+                        ct = e >> 8;
+                    }
+                    const uint32_t j = (uint32_t)__ffs((int)cur) - 1u;
+                    cur &= cur - 1u;
+                    const float4* rec4 = reinterpret_cast<const float4*>(stage + ct * L::WORDS);
+                    const float4 q5 = rec4[5];
+                    const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(q5.y));
+                    float frag[4];
+                    if (!MSAA) {
+                        float var[P::V > 0 ? P::V : 1];
+                        interpolate_smem<P>(rec4, (float)(segx0 + j), yf, var);
+                        P::fragment(u, p.samp, var, frag);
+                    } else {
+                        CornerCache lc, rc;
+                        lc.tri = rc.tri = NO_WINNER;
+                        msaa_fragment<P>(u, p.samp, reinterpret_cast<const float*>(rec4), __float_as_uint(q5.z), segx0 + j, y, band_lo, p.msaa_level, lc, rc, frag);
+                    }
+                    col_sm[j] = P::blend(col_sm[j], frag);
+                }
+                qn = 0; qf = 0;
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, own != 0u)) break;
         }
     }
 
+    // deferred fragment + blend: once per pixel, for the last triangle that passed
+    if (DEFER && row_ok && shade_px) {
+        uint32_t col[8];
+        if (vec_ok) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
+            col[0] = a.x; col[1] = a.y; col[2] = a.z; col[3] = a.w; col[4] = b.x; col[5] = b.y; col[6] = b.z; col[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) col[j] = segx0 + j < p.w ? p.pixel[base + j] : 0u;
+        }
+        CornerCache lc, rc;
+        lc.tri = rc.tri = NO_WINNER;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (cw[j] != NO_WINNER) {
+                const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)cw[j] * L::WORDS);
+                const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
+                float frag[4];
+                if (!MSAA) shade_at<P>(u, p.samp, rec, (float)(segx0 + j), yf, frag);
+                else msaa_fragment<P>(u, p.samp, rec, cw[j], segx0 + j, y, band_lo, p.msaa_level, lc, rc, frag);
+                col[j] = P::blend(col[j], frag);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cw[j] = col[j];
+    }
+
+    if (QUEUE && row_ok && shade_px) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cw[j] = col_sm[j];
+    }
     // write back
     if (row_ok) {
-        const size_t base = layer_off + (size_t)y * p.w + segx0;
         if (p.depth_write) {
-            if (full_seg && (p.w & 3u) == 0) {
+            if (vec_ok) {
                 *reinterpret_cast<float4*>(p.depth + base) = make_float4(depth[0], depth[1], depth[2], depth[3]);
                 *reinterpret_cast<float4*>(p.depth + base + 4) = make_float4(depth[4], depth[5], depth[6], depth[7]);
             } else {
@@ -656,13 +821,13 @@ template <class P, bool MSAA> __global__ void __launch_bounds__(RASTER_WARPS * 3
                 for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.depth[base + j] = depth[j];
             }
         }
-        if (P::HAS_FRAGMENT && p.pixel_write) {
-            if (full_seg && (p.w & 3u) == 0) {
-                *reinterpret_cast<uint4*>(p.pixel + base) = make_uint4(color[0], color[1], color[2], color[3]);
-                *reinterpret_cast<uint4*>(p.pixel + base + 4) = make_uint4(color[4], color[5], color[6], color[7]);
+        if (shade_px) {
+            if (vec_ok) {
+                *reinterpret_cast<uint4*>(p.pixel + base) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                *reinterpret_cast<uint4*>(p.pixel + base + 4) = make_uint4(cw[4], cw[5], cw[6], cw[7]);
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.pixel[base + j] = color[j];
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.pixel[base + j] = cw[j];
             }
         }
     }

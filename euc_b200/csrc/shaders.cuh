@@ -91,12 +91,14 @@ template <int C> __device__ __forceinline__ void sample2d(const SamplerDev& s, f
 //   vertex(u, vptr, clip, var)       Pipeline::vertex
 //   fragment(u, samp, var, frag)     Pipeline::fragment   (frag = Rgba<f32>)
 //   blend(old, frag)                 Pipeline::blend      (Pixel = u32)
+//   BLEND_IGNORES_OLD  blend does not read `old` (and fragment is pure): shading may be deferred to once per pixel
 // -------------------------------------------------------------------------------------------------------
 
 // benches/teapot.rs:10-51
 struct PipeTeapotShadow {
     static constexpr int V = 0;
     static constexpr bool HAS_FRAGMENT = false;
+    static constexpr bool BLEND_IGNORES_OLD = false;
     using Uniforms = euc_uniforms_teapot_shadow;
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_pn);
     static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float* var) {
@@ -111,6 +113,7 @@ struct PipeTeapotShadow {
 struct PipeTeapotPhong {
     static constexpr int V = 9;
     static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = true;
     using Uniforms = euc_uniforms_teapot_phong;
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_pn);
     static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float* var) {
@@ -163,6 +166,7 @@ struct PipeTeapotPhong {
 struct PipeTexCube {
     static constexpr int V = 2;
     static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = true;
     using Uniforms = euc_uniforms_tex_cube;
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_p4uv);
     static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float* var) {
@@ -183,6 +187,7 @@ struct PipeTexCube {
 struct PipeBlendTris {
     static constexpr int V = 4;
     static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = false;
     struct Uniforms { float _unused[4]; };
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_p4c4);
     static __device__ __forceinline__ void vertex(const Uniforms&, const uint8_t* vp, float4& clip, float* var) {
@@ -207,6 +212,7 @@ struct PipeBlendTris {
 struct PipeVoxelIcon {
     static constexpr int V = 7;
     static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = false;
     using Uniforms = euc_uniforms_voxel_icon;
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_voxel);
     static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float* var) {
@@ -239,6 +245,7 @@ struct PipeVoxelIcon {
 struct PipeVertexColor {
     static constexpr int V = 4;
     static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = true;
     using Uniforms = euc_uniforms_vertex_color;
     static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_p4c4);
     static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float* var) {
