@@ -640,19 +640,45 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
         const uint32_t* stage = recs_sm + (b & 1u) * STAGE_WORDS;
 
-        // lane t: which lanes (row, half) does triangle t's bounding box touch?
+        // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then a conservative edge test per
+        // (row, half): a weight that is negative at both ends of the segment by more than the rounding-error bound of
+        // euc's accumulated chain is negative on every pixel in between (the weights are linear in x).  Bound: the
+        // chain value after k additions differs from the closed form by at most (k + 4) * 2^-24 * M, with
+        // M <= |o + dy*y| + |dx| * x1; we use twice that.  NaN/Inf compare false and are therefore never rejected.
         uint32_t m = 0;
         if (lane < cnt) {
-            const uint32_t bbx = stage[lane * L::WORDS + R_BBX], bby = stage[lane * L::WORDS + R_BBY];
+            const float4* rec4 = reinterpret_cast<const float4*>(stage + lane * L::WORDS);
+            const float4 q4 = rec4[4];
+            const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
             const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
             const uint32_t ra = max(y0, tile_y0) - tile_y0, rb = min(y1, tile_y0 + TILE) - tile_y0;  // rows [ra, rb) of the tile
-            if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra) {
-                const uint32_t hi = rb >= 16u ? 0xffffffffu : ((1u << (2u * rb)) - 1u);
-                const uint32_t lo = (1u << (2u * ra)) - 1u;
-                uint32_t seg = 0;
-                if (x0 < tile_x0 + 8u && x1 > tile_x0) seg |= 0x55555555u;
-                if (x0 < tile_x0 + 16u && x1 > tile_x0 + 8u) seg |= 0xaaaaaaaau;
-                m = hi & ~lo & seg;
+            if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra && x1 > x0) {
+                const bool seg0 = x0 < tile_x0 + 8u && x1 > tile_x0, seg1 = x0 < tile_x0 + 16u && x1 > tile_x0 + 8u;
+                const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
+                const float kerr = (float)(x1 - x0 + 8u) * 1.1920929e-07f;  // (k + 8) * 2^-23
+                const float x1f = (float)x1;
+                const float mx0 = fabsf(q0.w) * x1f, mx1 = fabsf(q1.x) * x1f, mx2 = fabsf(q1.y) * x1f;
+                // segment end points clamped to the bounds: [xa, xb] inclusive pixel coordinates
+                const float xa0 = (float)max(tile_x0, x0), xb0 = (float)min(tile_x0 + 7u, x1 - 1u);
+                const float xa1 = (float)max(tile_x0 + 8u, x0), xb1 = (float)min(tile_x0 + 15u, x1 - 1u);
+                for (uint32_t r = ra; r < rb; ++r) {
+                    const float yr = (float)(tile_y0 + r);
+                    const float A0 = q0.x + q1.z * yr, A1 = q0.y + q1.w * yr, A2 = q0.z + q2.x * yr;
+                    const float m0 = kerr * (fabsf(A0) + mx0), m1 = kerr * (fabsf(A1) + mx1), m2 = kerr * (fabsf(A2) + mx2);
+                    const float mu = m0 + m1 + m2;
+#pragma unroll
+                    for (int sgi = 0; sgi < 2; ++sgi) {
+                        if (sgi == 0 ? seg0 : seg1) {
+                            const float xa = sgi == 0 ? xa0 : xa1, xb = sgi == 0 ? xb0 : xb1;
+                            const float fa0 = A0 + q0.w * xa, fb0 = A0 + q0.w * xb;
+                            const float fa1 = A1 + q1.x * xa, fb1 = A1 + q1.x * xb;
+                            const float fa2 = A2 + q1.y * xa, fb2 = A2 + q1.y * xb;
+                            const float ua = fa2 - fa0 - fa1, ub = fb2 - fb0 - fb1;
+                            const bool rej = (fa0 < -m0 && fb0 < -m0) || (fa1 < -m1 && fb1 < -m1) || (ua < -mu - mu && ub < -mu - mu);
+                            if (!rej) m |= 1u << (2u * r + (uint32_t)sgi);
+                        }
+                    }
+                }
             }
         }
         // transpose: own bit t <=> triangle t touches this lane
