@@ -51,7 +51,7 @@ struct euc_ctx {
     int sm_count = 148;
     uint64_t launches = 0;
     bool profiling = false;
-    cudaEvent_t ev[EUC_STAGE_COUNT + 1] = {};
+    cudaEvent_t ev_counts = nullptr;
     std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[EUC_STAGE_COUNT] = {};
@@ -155,46 +155,58 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * L::BYTES)) != EUC_OK) return rcode;
     prm.recs = (uint32_t*)ctx->recs.p;
 
+    // The pair list is sized optimistically (grow-only, from earlier renders or a guess) so that fill and raster can be
+    // queued before the host knows the pair count: the GPU never waits for the host.  alloc_tiles flags a list that is
+    // too small, fill/raster then exit immediately, and the host re-launches them after growing the list.
+    if ((rcode = ensure(ctx, ctx->tile_list, std::max<size_t>((size_t)prm.n_tris * 3, 1u << 16) * 4)) != EUC_OK) return rcode;
+    prm.tile_list = (uint32_t*)ctx->tile_list.p;
+    prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
+
     CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
+    const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
+    constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
+    const size_t smem = raster_smem_bytes<P>();
+    const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
+    auto kern = msaa ? raster_kernel<P, true, DEFER> : raster_kernel<P, false, DEFER>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[msaa]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[msaa] = true;
+    }
+    auto launch_fill_raster = [&]() {
+        { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+        { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
+    };
     { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
     { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
-    CU(cudaGetLastError());
-    // The pair count sizes the list; it is also where out-of-range indices are reported (reference: slice panic).
     CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev_counts, ctx->stream));
+    launch_fill_raster();
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(ctx->ev_counts));  // waits for setup + alloc only; fill and raster are already queued behind
     const unsigned long long pairs = ctx->counters_host[0];
-    if (ctx->counters_host[3] & 1ull) {
-        // tile_count was incremented by the setup pass: restore the all-zero invariant before bailing out
-        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
-        return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
-    }
     ctx->last.primitives = prm.n_tris;
     ctx->last.binned_pairs = pairs;
     ctx->last.fragments = 0;
-    if (pairs == 0) return EUC_OK;
-    if (pairs > 0xfffffff0ull) return fail(ctx, EUC_E_UNSUPPORTED, "too many (tile, primitive) pairs: %llu", pairs);
-    if ((rcode = ensure(ctx, ctx->tile_list, (size_t)pairs * 4)) != EUC_OK) return rcode;
-    prm.tile_list = (uint32_t*)ctx->tile_list.p;
-    prm.list_capacity = (uint32_t)(ctx->tile_list.cap / 4);
-
-    { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
-    { StageTimer t(ctx, EUC_STAGE_SORT); sort_lists_kernel<<<(n_tiles + 3) / 4, 128, 0, ctx->stream>>>(prm, n_tiles); }
-    const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
-    {
-        constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
-        const size_t smem = raster_smem_bytes<P>();
-        const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
-        auto kern = msaa ? raster_kernel<P, true, DEFER> : raster_kernel<P, false, DEFER>;
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[msaa]) {
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[msaa] = true;
-        }
-        StageTimer t(ctx, EUC_STAGE_RASTER);
-        kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles);
+    if (ctx->counters_host[3] & 1ull) {
+        // reference: slice index panic (index.rs:53).  fill/raster skipped themselves; restore the all-zero tile counters.
+        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
+        return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
     }
-    CU(cudaGetLastError());
+    if (ctx->counters_host[3] & 2ull) {
+        if (pairs > 0xfffffff0ull) {
+            CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
+            return fail(ctx, EUC_E_UNSUPPORTED, "too many (tile, primitive) pairs: %llu", pairs);
+        }
+        if ((rcode = ensure(ctx, ctx->tile_list, (size_t)pairs * 4)) != EUC_OK) return rcode;
+        prm.tile_list = (uint32_t*)ctx->tile_list.p;
+        prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
+        unsigned long long zero = 0;
+        CU(cudaMemcpyAsync(ctx->counters + 3, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+        launch_fill_raster();
+        CU(cudaGetLastError());
+    }
     return EUC_OK;
 }
 
@@ -365,6 +377,7 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
         delete ctx;
         return EUC_E_CUDA;
     }
+    if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     *out_ctx = ctx;
     return EUC_OK;
@@ -380,6 +393,7 @@ int euc_shutdown(euc_ctx* ctx) {
     for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx};
     for (Scratch* s : ss) cudaFree(s->p);
+    cudaEventDestroy(ctx->ev_counts);
     cudaFree(ctx->counters);
     cudaFreeHost(ctx->counters_host);
     cudaStreamDestroy(ctx->own);

@@ -5,8 +5,7 @@
 //                               population count.  One thread per triangle; emits a fixed-size setup record.
 //   K3     alloc_tiles_kernel   gives every non-empty 16x16 tile a private slice of the pair list
 //          fill_kernel          writes (tile <- triangle) pairs
-//          sort_lists_kernel    restores submission order inside every tile list (src/pipeline.rs:581 semantics)
-//   K4/K5  raster_kernel<P>     one warp per tile: lane = half a tile row (8 px); colour and depth of the tile live
+//   K4/K5  raster_kernel<P>     one warp per tile; restores submission order inside the tile's list (pipeline.rs:581), then: lane = half a tile row (8 px); colour and depth of the tile live
 //                               in registers for the whole list; setup records stream into shared memory through
 //                               cp.async.bulk + mbarrier; coverage, depth test, fragment shade (incl. euc's
 //                               coarse-shading "MSAA"), blend in submission order (triangles.rs:219-303,
@@ -326,9 +325,16 @@ __global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant_
     if (lane == 31 && total) base = atomicAdd(p.counters + 2, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (t < n_tiles) p.tile_range[t] = make_uint2((uint32_t)base + incl - n, n);
+    // the pair total is final here (setup has completed): flag a list that is too small for this render
+    if (t == 0 && p.counters[0] > (unsigned long long)p.list_capacity) atomicOr(p.counters + 3, 2ull);
 }
 
+// Non-zero when this render must not proceed: a vertex index was out of range (bit 0) or the pair list is too small
+// (bit 1).  Written before fill/raster start (stream order); the host re-launches them after growing the list.
+__device__ __forceinline__ bool render_aborted(const Params& p) { return (*(volatile unsigned long long*)(p.counters + 3) & 3ull) != 0ull; }
+
 __global__ void __launch_bounds__(128) fill_kernel(const __grid_constant__ Params p) {
+    if (render_aborted(p)) return;
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tri < p.n_tris;
     uint2 bbox = live ? p.tri_bbox[tri] : make_uint2(0u, 0u);
@@ -342,8 +348,9 @@ __global__ void __launch_bounds__(128) fill_kernel(const __grid_constant__ Param
     });
 }
 
-// One warp per tile.  Lists of up to 32 entries are sorted in registers (bitonic network over lanes); up to
-// SORT_SMEM entries in shared memory; longer ones in place in global memory.
+// Tile lists are filled with atomics, i.e. in arbitrary order; the raster kernel restores submission order (ascending
+// primitive index, src/pipeline.rs:581 semantics) before it walks a list: in registers for up to 128 entries, in
+// shared memory for up to SORT_SMEM, in place in global memory beyond that.
 constexpr int SORT_SMEM = 2048;
 __device__ __forceinline__ void bitonic_mem(uint32_t* a, uint32_t n_pow2, uint32_t lane) {
     for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
@@ -360,50 +367,33 @@ __device__ __forceinline__ void bitonic_mem(uint32_t* a, uint32_t n_pow2, uint32
         }
     }
 }
-__global__ void __launch_bounds__(128) sort_lists_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
-    __shared__ uint32_t sm[4][SORT_SMEM];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t tile = blockIdx.x * 4 + warp;
-    if (tile >= n_tiles) return;
-    const uint2 rg = p.tile_range[tile];
-    const uint32_t n = rg.y;
-    if (n <= 1) return;
-    uint32_t* list = p.tile_list + rg.x;
-    if (n <= 32) {
-        uint32_t v = lane < n ? list[lane] : 0xffffffffu;
+// Sorts the n <= 128 ids held 4 per lane (element index = r * 32 + lane, padded with 0xffffffff) ascending.
+__device__ __forceinline__ void bitonic_regs128(uint32_t (&v)[4], uint32_t lane) {
 #pragma unroll
-        for (uint32_t k = 2; k <= 32; k <<= 1) {
+    for (uint32_t k = 2; k <= 128; k <<= 1) {
 #pragma unroll
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
-                bool up = (lane & k) == 0, lower = (lane & j) == 0;
-                v = (lower == up) ? min(v, o) : max(v, o);
-            }
-        }
-        if (lane < n) list[lane] = v;
-        return;
-    }
-    uint32_t np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    if (np2 <= SORT_SMEM) {
-        uint32_t* a = sm[warp];
-        for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? list[i] : 0xffffffffu;
-        __syncwarp();
-        bitonic_mem(a, np2, lane);
-        for (uint32_t i = lane; i < n; i += 32u) list[i] = a[i];
-    } else {
-        // Global fallback: odd-even transposition is too slow; use bitonic with virtual padding (out-of-range = +inf).
-        for (uint32_t k = 2; k <= np2; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = lane; i < np2; i += 32u) {
-                    uint32_t ixj = i ^ j;
-                    if (ixj > i) {
-                        uint32_t x = i < n ? list[i] : 0xffffffffu, y = ixj < n ? list[ixj] : 0xffffffffu;
-                        bool up = (i & k) == 0;
-                        if ((x > y) == up) { if (i < n) list[i] = y; if (ixj < n) list[ixj] = x; }
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // partner lives in the same lane, register r ^ (j / 32)
+                const uint32_t dr = j >> 5;
+#pragma unroll
+                for (uint32_t r = 0; r < 4; ++r) {
+                    if ((r & dr) == 0) {
+                        const uint32_t i = r * 32;  // (i & k) only depends on r here because k > 32
+                        const bool up = (i & k) == 0;
+                        const uint32_t a = v[r], b = v[r | dr];
+                        const uint32_t lo = min(a, b), hi = max(a, b);
+                        v[r] = up ? lo : hi;
+                        v[r | dr] = up ? hi : lo;
                     }
                 }
-                __syncwarp();
+            } else {
+#pragma unroll
+                for (uint32_t r = 0; r < 4; ++r) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const uint32_t i = r * 32 + lane;
+                    const bool up = (i & k) == 0, lower = (lane & j) == 0;
+                    v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+                }
             }
         }
     }
@@ -463,6 +453,8 @@ constexpr int Q_ENTRIES = 12;     // entries per lane (u16), lane stride 7 words
 constexpr int Q_STRIDE_WORDS = 7;
 constexpr int Q_FRAGS = 20;       // stop generating once a lane holds this many fragments
 constexpr int COL_STRIDE = 9;     // colour row of a lane: 8 words + 1 pad
+
+constexpr int IDS_REGS = 128;      // lists up to this length are sorted, and then kept, in registers (4 per lane)
 
 template <class P> constexpr size_t raster_smem_bytes() {
     return (size_t)RASTER_WARPS * (2 * BATCH * RecLayout<P>::BYTES + 16 + 32 * (Q_STRIDE_WORDS + COL_STRIDE) * 4);
@@ -567,11 +559,56 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    if (tile >= n_tiles) return;
+    if (tile >= n_tiles || render_aborted(p)) return;
     const uint2 rg = p.tile_range[tile];
     const uint32_t n = rg.y;
     if (n == 0) return;
-    const uint32_t* __restrict__ list = p.tile_list + rg.x;
+    // restore submission order inside this tile's list (the fill pass appended with atomics)
+    // Short lists: sorted element r*32+lane ends up in register v[r] of this lane, which is exactly the id this lane
+    // needs when it issues the bulk copy of batch r.  Long lists are sorted in place and read back from global memory.
+    const bool short_list = n <= (uint32_t)IDS_REGS;
+    uint32_t* const list = p.tile_list + rg.x;
+    uint32_t v[4];
+    if (short_list) {
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) v[r] = r * 32 + lane < n ? list[r * 32 + lane] : 0xffffffffu;
+        if (n > 1) bitonic_regs128(v, lane);
+    } else {
+        uint32_t np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        if (np2 <= (uint32_t)SORT_SMEM && np2 <= 2u * STAGE_WORDS) {
+            uint32_t* a = recs_sm;  // the record stages are not in use yet
+            for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? list[i] : 0xffffffffu;
+            __syncwarp();
+            bitonic_mem(a, np2, lane);
+            for (uint32_t i = lane; i < n; i += 32u) list[i] = a[i];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above, bulk-copy writes below
+        } else {
+            // In place in global memory, any n: the all-ascending bitonic network (first step of every merge pairs i
+            // with i ^ (k-1), the rest with i ^ j; the lower index always receives the minimum).  Elements past n act as
+            // +inf, never move below n, so pairs that reach past n are simply skipped.
+            auto cmpx = [&](uint32_t i, uint32_t partner) {
+                if (partner > i && partner < n) {
+                    const uint32_t x = list[i], y2 = list[partner];
+                    if (x > y2) { list[i] = y2; list[partner] = x; }
+                }
+            };
+            for (uint32_t k = 2; k <= np2; k <<= 1) {
+                for (uint32_t i = lane; i < n; i += 32u) cmpx(i, i ^ (k - 1u));
+                __syncwarp();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < n; i += 32u) cmpx(i, i ^ j);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+    }
+    auto batch_id = [&](uint32_t b) -> uint32_t {  // id of element b*32+lane of the sorted list (0 past the end)
+        if (short_list) return b == 0 ? v[0] : (b == 1 ? v[1] : (b == 2 ? v[2] : v[3]));
+        const uint32_t pos = b * BATCH + lane;
+        return pos < n ? list[pos] : 0u;
+    };
 
     // tile / lane geometry
     const uint32_t tiles_per_layer = p.tiles_x * p.tiles_y;
@@ -625,16 +662,15 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         __syncwarp();
         if (lane < cnt) bulk_g2s(recs_sm + (b & 1u) * STAGE_WORDS + lane * L::WORDS, p.recs + (size_t)id * L::WORDS, (uint32_t)L::BYTES, mb);
     };
-    uint32_t id_pf = lane < n ? __ldg(list + lane) : 0u;
+    uint32_t id_pf = batch_id(0);
     issue(0, id_pf);
-    id_pf = (BATCH + lane < n) ? __ldg(list + BATCH + lane) : 0u;
+    id_pf = n_batches > 1 ? batch_id(1) : 0u;
 
     for (uint32_t b = 0; b < n_batches; ++b) {
         __syncwarp();  // every lane is done with stage (b+1)&1 (read in iteration b-1)
         if (b + 1 < n_batches) {
             issue(b + 1, id_pf);
-            const uint32_t pos = (b + 2) * BATCH + lane;
-            id_pf = pos < n ? __ldg(list + pos) : 0u;
+            id_pf = b + 2 < n_batches ? batch_id(b + 2) : 0u;
         }
         mbar_wait(&bar[b & 1u], (b >> 1) & 1u);
         const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);

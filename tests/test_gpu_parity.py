@@ -248,3 +248,52 @@ def test_quirks_and_errors():
     rpx, rz = np.zeros((640, 64), dtype=np.uint32), np.full((640, 64), 1.0, dtype=np.float32)
     oracle.render(e.BlendTris(), verts[:29], rpx, rz)
     assert_depth_bit_exact(z.raw(), rz, "partial primitive")
+
+
+def test_pair_list_overflow_relaunch():
+    """A fresh context sizes the (tile, primitive) list optimistically; full-screen triangles overflow that guess, the
+    device flags it, and the host re-launches fill + raster after growing the list.  Results must be unaffected."""
+    ctx = e.Context(0)
+    w, h = 1024, 768
+    n = 300
+    r = scenes.u01(99, n * 3 * 8).reshape(n, 3, 8)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    v["pos"][:, :, 0] = np.array([-1.5, 1.5, 0.0])[None, :] + (r[:, :, 0] - 0.5) * 0.2
+    v["pos"][:, :, 1] = np.array([-1.5, -1.5, 1.5])[None, :] + (r[:, :, 1] - 0.5) * 0.2
+    v["pos"][:, :, 2] = r[:, :, 2]
+    v["pos"][:, :, 3] = 1.0
+    v["rgba"][:, :, :3] = r[:, :, 3:6]
+    v["rgba"][:, :, 3] = 0.5
+    v = v.reshape(-1)
+    px = e.Buffer2d.fill([w, h], 0xFF000000, dtype=np.uint32, ctx=ctx)
+    z = e.Buffer2d.fill([w, h], 1.0, ctx=ctx)
+    ctx.set_stats(True)
+    e.BlendTris().render(v, px, z)
+    st = ctx.get_stats()
+    assert st["binned_pairs"] > (1 << 16), "scene must overflow the initial list guess"
+    rpx, rz = np.full((h, w), 0xFF000000, np.uint32), np.full((h, w), 1.0, np.float32)
+    rs = oracle.render(e.BlendTris(), v, rpx, rz, n_threads=0)
+    assert st["fragments"] == rs["fragments"]
+    assert_depth_bit_exact(z.raw(), rz, "overflow relaunch")
+    assert_colour_within_1lsb(px.raw(), rpx, "overflow relaunch")
+    del px, z
+    ctx.close()
+
+
+def test_long_tile_lists_sorted():
+    """Many small triangles stacked on the same tile: list lengths beyond the register sort (128) and the
+    shared-memory sort (2048) paths; blending makes the result order-sensitive."""
+    w, h = 640, 64
+    for n in (100, 700, 3000):
+        r = scenes.u01(1234 + n, n * 3 * 8).reshape(n, 3, 8)
+        v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+        v["pos"][:, :, 0] = -0.9 + r[:, :, 0] * 0.08
+        v["pos"][:, :, 1] = 0.2 + r[:, :, 1] * 0.6
+        v["pos"][:, :, 2] = 0.9 - 0.8 * (np.arange(n)[:, None] / n) + r[:, :, 2] * 1e-4   # later triangles are nearer: all pass
+        v["pos"][:, :, 3] = 1.0
+        v["rgba"][:, :, :3] = r[:, :, 3:6]
+        v["rgba"][:, :, 3] = 0.3
+        gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), v.reshape(-1), w, h, clear_px=0xFF000000)
+        assert_depth_bit_exact(gz, rz, f"long list {n}")
+        assert_colour_within_1lsb(gpx, rpx, f"long list {n}")
+        assert gs["fragments"] == rs["fragments"] > n
