@@ -282,6 +282,16 @@ def run_ours(args, rank, world, local_rank):
             if rank == 0:
                 host_out.copy_(gather[: h * w], non_blocking=True)
 
+        def verify():
+            """N-GPU (or 1-GPU) frame against the oracle-generated golden CRC at full size (bit-exact: this shader has no
+            transcendental)."""
+            import zlib
+            frame()
+            torch.cuda.synchronize()
+            got = gather[: h * w].cpu().numpy().view(np.uint32)
+            gold = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+            return bool(zlib.crc32(got.tobytes()) == int(gold["c4_color_crc"]))
+
         h2d, d2h = pv.numel() + pi.numel(), h * w * 4
         config_extra = {"partition": f"{world} row band(s) of {slot_rows} rows + NCCL all_gather of colour rows" if world > 1 else "single GPU",
                         "l2": "working set (80 MB geometry + 151 MB setup records + 66 MB targets) > 126 MB L2; no flush"}
@@ -426,6 +436,7 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = timed(frame_e2e, e2e_steps, flush_buf)
     clocks = sampler.result()
 
+    verified = verify() if wl == "c4" else None  # collective inside: every rank calls it
     frames_per_step = 1 if wl != "c5" else scene["n_icons"] * world
     job_mult = 1 if wl in ("c4", "c5") else world  # replicas render independent frames
     value = frames_per_step * job_mult * steps / (ms / 1000.0)
@@ -466,6 +477,8 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": peak_src, "frame_frac": (alg / ((ms / steps) / 1000.0) / 1e9) / peak if wl != "c5" else None},
             "stage_ms_per_launch": stage_ms,
         }
+        if verified is not None:
+            line["frame_matches_golden_crc"] = verified
         if world == 1 and not args.no_cpu_baseline:
             try:
                 run, scale, desc, cores = cpu_plan(wl, scene)
