@@ -632,6 +632,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
     uint32_t cw[8];  // colour (immediate mode) or winning triangle id (deferred mode)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { depth[j] = 0.0f; cw[j] = DEFER ? NO_WINNER : 0u; }
+    // Fast depth modes: LESS and GREATER share one comparison by keeping sgn*depth in the registers (sgn = -1 for
+    // GREATER; negation is exact and NaN stays NaN, so `sgn*z < sgn*old` has exactly partial_cmp's outcome).
+    const bool fast_depth = p.depth_test == EUC_DEPTH_LESS || p.depth_test == EUC_DEPTH_GREATER;
+    const float dsgn = p.depth_test == EUC_DEPTH_GREATER ? -1.0f : 1.0f;
     if (row_ok && p.uses_depth) {
         if (vec_ok) {
             const float4 a = *reinterpret_cast<const float4*>(p.depth + base), b = *reinterpret_cast<const float4*>(p.depth + base + 4);
@@ -640,6 +644,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) depth[j] = p.depth[base + j];
         }
+    }
+    if (fast_depth) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) depth[j] = depth[j] * dsgn;
     }
     if (QUEUE && row_ok && shade_px) {
         if (vec_ok) {
@@ -780,6 +788,25 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
                 const bool zc = p.zclip && (__float_as_uint(q5.x) & 1u) == 0u;  // per-fragment z clip needed (:271)
                 const uint32_t tri_id = __float_as_uint(q5.z);
                 uint32_t passmask = 0;
+                if (fast_depth) {
+                    // z clip as bounds: when every vertex passed the clip the per-fragment test is skipped (:271), i.e.
+                    // the bounds are infinite.  A NaN z fails here but would fail the depth comparison anyway.
+                    const float zlo = zc ? p.zmin : -__int_as_float(0x7f800000), zhi = zc ? p.zmax : __int_as_float(0x7f800000);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float wu2 = w2 - w0 - w1;                                          // :264
+                        const float z = z0 * w0 + z1 * w1 + z2 * wu2;                            // :269
+                        const float zs = z * dsgn;
+                        const bool pass = ((inmask >> j) & 1u) && w0 >= 0.0f && w1 >= 0.0f && wu2 >= 0.0f &&  // :262, :267
+                                          zlo <= z && z <= zhi && zs < depth[j];                 // :271, pipeline.rs:519-526
+                        if (pass) {
+                            passmask |= 1u << j;
+                            if (p.depth_write) depth[j] = zs;                                    // pipeline.rs:536-538
+                            if (DEFER) cw[j] = tri_id;
+                        }
+                        if ((uint32_t)j >= jlo) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; } // :301
+                    }
+                } else
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float wu2 = w2 - w0 - w1;                                              // :264
@@ -873,6 +900,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         for (int j = 0; j < 8; ++j) cw[j] = col_sm[j];
     }
     // write back
+    if (fast_depth) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) depth[j] = depth[j] * dsgn;
+    }
     if (row_ok) {
         if (p.depth_write) {
             if (vec_ok) {
