@@ -684,11 +684,13 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
         const uint32_t* stage = recs_sm + (b & 1u) * STAGE_WORDS;
 
-        // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then a conservative edge test per
-        // (row, half): a weight that is negative at both ends of the segment by more than the rounding-error bound of
-        // euc's accumulated chain is negative on every pixel in between (the weights are linear in x).  Bound: the
-        // chain value after k additions differs from the closed form by at most (k + 4) * 2^-24 * M, with
-        // M <= |o + dy*y| + |dx| * x1; we use twice that.  NaN/Inf compare false and are therefore never rejected.
+        // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then per tile row the range of
+        // integer x on which all three weights can be non-negative.  Each weight is linear in x (w = A + d*x); euc
+        // evaluates it by an accumulated chain whose value after k additions differs from the closed form by at most
+        // (k + 4) * 2^-24 * M with M <= |A| + |d| * x1.  We solve A + d*x >= -m with m at least twice that bound (so the
+        // range is a superset of every pixel the chain can accept), widen by a slack for the rounding of the solve
+        // itself (reciprocal + product: relative 2^-22 of |x| <= x1), and intersect the three ranges.  NaN compares
+        // false everywhere and therefore never constrains or rejects.
         uint32_t m = 0;
         if (lane < cnt) {
             const float4* rec4 = reinterpret_cast<const float4*>(stage + lane * L::WORDS);
@@ -699,29 +701,32 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
             if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra && x1 > x0) {
                 const bool seg0 = x0 < tile_x0 + 8u && x1 > tile_x0, seg1 = x0 < tile_x0 + 16u && x1 > tile_x0 + 8u;
                 const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
+                const float d0 = q0.w, d1 = q1.x, d2 = q1.y, du = d2 - d0 - d1;
+                const float i0 = 1.0f / d0, i1 = 1.0f / d1, iu = 1.0f / du;
                 const float kerr = (float)(x1 - x0 + 8u) * 1.1920929e-07f;  // (k + 8) * 2^-23
                 const float x1f = (float)x1;
-                const float mx0 = fabsf(q0.w) * x1f, mx1 = fabsf(q1.x) * x1f, mx2 = fabsf(q1.y) * x1f;
+                const float mx0 = fabsf(d0) * x1f, mx1 = fabsf(d1) * x1f, mx2 = fabsf(d2) * x1f;
                 // segment end points clamped to the bounds: [xa, xb] inclusive pixel coordinates
                 const float xa0 = (float)max(tile_x0, x0), xb0 = (float)min(tile_x0 + 7u, x1 - 1u);
                 const float xa1 = (float)max(tile_x0 + 8u, x0), xb1 = (float)min(tile_x0 + 15u, x1 - 1u);
+                const float slack = 0.01f + x1f * 1e-5f;
+                const float BIG = 3.0e38f;
                 for (uint32_t r = ra; r < rb; ++r) {
                     const float yr = (float)(tile_y0 + r);
                     const float A0 = q0.x + q1.z * yr, A1 = q0.y + q1.w * yr, A2 = q0.z + q2.x * yr;
                     const float m0 = kerr * (fabsf(A0) + mx0), m1 = kerr * (fabsf(A1) + mx1), m2 = kerr * (fabsf(A2) + mx2);
-                    const float mu = m0 + m1 + m2;
-#pragma unroll
-                    for (int sgi = 0; sgi < 2; ++sgi) {
-                        if (sgi == 0 ? seg0 : seg1) {
-                            const float xa = sgi == 0 ? xa0 : xa1, xb = sgi == 0 ? xb0 : xb1;
-                            const float fa0 = A0 + q0.w * xa, fb0 = A0 + q0.w * xb;
-                            const float fa1 = A1 + q1.x * xa, fb1 = A1 + q1.x * xb;
-                            const float fa2 = A2 + q1.y * xa, fb2 = A2 + q1.y * xb;
-                            const float ua = fa2 - fa0 - fa1, ub = fb2 - fb0 - fb1;
-                            const bool rej = (fa0 < -m0 && fb0 < -m0) || (fa1 < -m1 && fb1 < -m1) || (ua < -mu - mu && ub < -mu - mu);
-                            if (!rej) m |= 1u << (2u * r + (uint32_t)sgi);
-                        }
-                    }
+                    const float mu = 2.0f * (m0 + m1 + m2);
+                    const float Au = A2 - A0 - A1;
+                    const float t0 = (-m0 - A0) * i0, t1 = (-m1 - A1) * i1, tu = (-mu - Au) * iu;
+                    // d > 0: x >= t;  d < 0: x <= t;  d == 0: the whole row is out when A < -m
+                    float lo = d0 > 0.0f ? t0 : -BIG, hi = d0 < 0.0f ? t0 : BIG;
+                    lo = fmaxf(lo, d1 > 0.0f ? t1 : -BIG); hi = fminf(hi, d1 < 0.0f ? t1 : BIG);
+                    lo = fmaxf(lo, du > 0.0f ? tu : -BIG); hi = fminf(hi, du < 0.0f ? tu : BIG);
+                    const bool dead = (d0 == 0.0f && A0 < -m0) || (d1 == 0.0f && A1 < -m1) || (du == 0.0f && Au < -mu);
+                    const float ilo = ceilf(lo - slack), ihi = floorf(hi + slack);  // integer pixel range that can pass
+                    const bool ok0 = seg0 && !dead && fmaxf(xa0, ilo) <= fminf(xb0, ihi);
+                    const bool ok1 = seg1 && !dead && fmaxf(xa1, ilo) <= fminf(xb1, ihi);
+                    m |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2u * r);
                 }
             }
         }
