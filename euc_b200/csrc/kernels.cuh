@@ -662,27 +662,22 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
     }
 
     uint32_t nfrag = 0;
-    const uint32_t n_batches = (n + BATCH - 1) / BATCH;
-    auto issue = [&](uint32_t b, uint32_t id) {  // lane i < cnt copies record i of batch b
-        const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
-        uint64_t* mb = &bar[b & 1u];
-        if (lane == 0) mbar_expect_tx(mb, cnt * (uint32_t)L::BYTES);
+    // Records are processed in rounds of ROUND = 2*BATCH: both record stages are filled, then every lane walks its own
+    // primitives of the round.  Longer rounds bring the busiest lane closer to the mean (the round ends when the last
+    // lane is done); the load of the next round is hidden by the other warps of the SM.
+    constexpr uint32_t ROUND = 2 * BATCH;
+    const uint32_t n_rounds = (n + ROUND - 1) / ROUND;
+    for (uint32_t rd = 0; rd < n_rounds; ++rd) {
+        __syncwarp();  // every lane is done with the records of the previous round
+        const uint32_t cnt = min(ROUND, n - rd * ROUND);
+        const uint32_t cnt0 = min(cnt, (uint32_t)BATCH), cnt1 = cnt - cnt0;
+        const uint32_t id0 = batch_id(2u * rd), id1 = cnt1 ? batch_id(2u * rd + 1u) : 0u;
+        if (lane == 0) mbar_expect_tx(&bar[0], cnt * (uint32_t)L::BYTES);
         __syncwarp();
-        if (lane < cnt) bulk_g2s(recs_sm + (b & 1u) * STAGE_WORDS + lane * L::WORDS, p.recs + (size_t)id * L::WORDS, (uint32_t)L::BYTES, mb);
-    };
-    uint32_t id_pf = batch_id(0);
-    issue(0, id_pf);
-    id_pf = n_batches > 1 ? batch_id(1) : 0u;
-
-    for (uint32_t b = 0; b < n_batches; ++b) {
-        __syncwarp();  // every lane is done with stage (b+1)&1 (read in iteration b-1)
-        if (b + 1 < n_batches) {
-            issue(b + 1, id_pf);
-            id_pf = b + 2 < n_batches ? batch_id(b + 2) : 0u;
-        }
-        mbar_wait(&bar[b & 1u], (b >> 1) & 1u);
-        const uint32_t cnt = min((uint32_t)BATCH, n - b * BATCH);
-        const uint32_t* stage = recs_sm + (b & 1u) * STAGE_WORDS;
+        if (lane < cnt0) bulk_g2s(recs_sm + lane * L::WORDS, p.recs + (size_t)id0 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
+        if (lane < cnt1) bulk_g2s(recs_sm + (BATCH + lane) * L::WORDS, p.recs + (size_t)id1 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
+        mbar_wait(&bar[0], rd & 1u);
+        const uint32_t* stage = recs_sm;
 
         // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then per tile row the range of
         // integer x on which all three weights can be non-negative.  Each weight is linear in x (w = A + d*x); euc
@@ -691,9 +686,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         // range is a superset of every pixel the chain can accept), widen by a slack for the rounding of the solve
         // itself (reciprocal + product: relative 2^-22 of |x| <= x1), and intersect the three ranges.  NaN compares
         // false everywhere and therefore never constrains or rejects.
+        auto lane_mask = [&](uint32_t ri, bool valid) -> uint32_t {
         uint32_t m = 0;
-        if (lane < cnt) {
-            const float4* rec4 = reinterpret_cast<const float4*>(stage + lane * L::WORDS);
+        if (valid) {
+            const float4* rec4 = reinterpret_cast<const float4*>(stage + ri * L::WORDS);
             const float4 q4 = rec4[4];
             const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
             const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
@@ -730,21 +726,28 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
                 }
             }
         }
-        // transpose: own bit t <=> triangle t touches this lane
-        uint32_t own = 0;
+        return m;
+        };
+        // transpose: own bit t <=> primitive t of the round touches this lane
+        auto transpose = [&](uint32_t m) -> uint32_t {
+            uint32_t own = 0;
 #pragma unroll
-        for (int l = 0; l < 32; ++l) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, (m >> l) & 1u);
-            if ((int)lane == l) own = bits;
-        }
-        if (!row_ok) own = 0;
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t bits = __ballot_sync(0xffffffffu, (m >> l) & 1u);
+                if ((int)lane == l) own = bits;
+            }
+            return row_ok ? own : 0u;
+        };
+        uint32_t own0 = transpose(lane_mask(lane, lane < cnt0));
+        uint32_t own1 = cnt1 ? transpose(lane_mask(BATCH + lane, lane < cnt1)) : 0u;
 
         uint32_t qn = 0, qf = 0;  // queued entries / fragments of this lane
         for (;;) {
             // ---- generate: coverage + depth for this lane's own triangles, until its FIFO is nearly full ----
-            while (own && qn < (uint32_t)Q_ENTRIES && qf < (uint32_t)Q_FRAGS) {
-                const uint32_t t = (uint32_t)__ffs((int)own) - 1u;
-                own &= own - 1u;
+            while ((own0 | own1) && qn < (uint32_t)Q_ENTRIES && qf < (uint32_t)Q_FRAGS) {
+                uint32_t t;
+                if (own0) { t = (uint32_t)__ffs((int)own0) - 1u; own0 &= own0 - 1u; }
+                else { t = (uint32_t)BATCH + (uint32_t)__ffs((int)own1) - 1u; own1 &= own1 - 1u; }
                 const float4* rec4 = reinterpret_cast<const float4*>(stage + t * L::WORDS);
                 const float4 q4 = rec4[4];  // c.x c.y bbx bby
                 const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
@@ -869,7 +872,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
                 qn = 0; qf = 0;
             }
             __syncwarp();
-            if (!__any_sync(0xffffffffu, own != 0u)) break;
+            if (!__any_sync(0xffffffffu, (own0 | own1) != 0u)) break;
         }
     }
 
