@@ -52,6 +52,7 @@ struct euc_ctx {
     uint64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev_counts = nullptr;
+    std::unordered_map<uint32_t, uint32_t> bin_cap_hint;  // per tile-count: bin size of the fast path (0 = use the exact path)
     std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[EUC_STAGE_COUNT] = {};
@@ -155,14 +156,6 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * L::BYTES)) != EUC_OK) return rcode;
     prm.recs = (uint32_t*)ctx->recs.p;
 
-    // The pair list is sized optimistically (grow-only, from earlier renders or a guess) so that fill and raster can be
-    // queued before the host knows the pair count: the GPU never waits for the host.  alloc_tiles flags a list that is
-    // too small, fill/raster then exit immediately, and the host re-launches them after growing the list.
-    if ((rcode = ensure(ctx, ctx->tile_list, std::max<size_t>((size_t)prm.n_tris * 3, 1u << 16) * 4)) != EUC_OK) return rcode;
-    prm.tile_list = (uint32_t*)ctx->tile_list.p;
-    prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
-
-    CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
     constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
@@ -174,14 +167,65 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[msaa] = true;
     }
+    auto launch_raster = [&]() { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); };
+    auto fetch_counters = [&]() -> int {  // asynchronous copy + event; the caller waits on the event
+        CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_counts, ctx->stream));
+        return EUC_OK;
+    };
+
+    // ---- fast path: fixed-capacity bins.  setup appends primitive ids straight into tile*cap + slot; raster follows.
+    // The capacity is a per-context hint (longest list seen, with headroom).  A tile that overflows flags the render;
+    // raster then exits at once and the whole render is redone on the exact path below.
+    uint32_t cap = 128;
+    {
+        auto it = ctx->bin_cap_hint.find(n_tiles);
+        if (it != ctx->bin_cap_hint.end()) cap = it->second;
+    }
+    const bool fast = cap > 0 && (size_t)n_tiles * cap * 4 <= ((size_t)1 << 30);
+    if (fast) {
+        if ((rcode = ensure(ctx, ctx->tile_list, (size_t)n_tiles * cap * 4)) != EUC_OK) return rcode;
+        prm.tile_list = (uint32_t*)ctx->tile_list.p;
+        prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
+        prm.bin_cap = cap;
+        CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+        if ((rcode = fetch_counters()) != EUC_OK) return rcode;
+        launch_raster();
+        CU(cudaGetLastError());
+        CU(cudaEventSynchronize(ctx->ev_counts));  // waits for setup only; raster is already queued behind it
+        ctx->last.primitives = prm.n_tris;
+        ctx->last.binned_pairs = ctx->counters_host[0];
+        ctx->last.fragments = 0;
+        if (ctx->counters_host[3] & 1ull) {
+            CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
+            return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
+        }
+        if (!(ctx->counters_host[3] & 2ull)) return EUC_OK;
+        // overflow: raster skipped itself.  Reset the tile counters and fall through to the exact path, which also
+        // measures the longest list for the next render's capacity.
+        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
+        ctx->bin_cap_hint[n_tiles] = 0;
+    }
+
+    // ---- exact path: count (setup) -> alloc -> fill -> raster.  The pair list is sized optimistically (grow-only) so
+    // that fill and raster can be queued before the host knows the pair count: the GPU never waits for the host.
+    // alloc_tiles flags a list that is too small, fill/raster then exit immediately, and the host re-launches them.
+    prm.bin_cap = 0;
+    if ((rcode = ensure(ctx, ctx->tile_list, std::max<size_t>((size_t)prm.n_tris * 3, 1u << 16) * 4)) != EUC_OK) return rcode;
+    prm.tile_list = (uint32_t*)ctx->tile_list.p;
+    prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
+
+    CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     auto launch_fill_raster = [&]() {
         { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
-        { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
+        launch_raster();
     };
     { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
     { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
-    CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(ctx->ev_counts, ctx->stream));
+    if ((rcode = fetch_counters()) != EUC_OK) return rcode;
+    // counters[1] held the longest list for the host; raster accumulates the fragment count there
+    CU(cudaMemsetAsync(ctx->counters + 1, 0, sizeof(unsigned long long), ctx->stream));
     launch_fill_raster();
     CU(cudaGetLastError());
     CU(cudaEventSynchronize(ctx->ev_counts));  // waits for setup + alloc only; fill and raster are already queued behind
@@ -193,6 +237,11 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         // reference: slice index panic (index.rs:53).  fill/raster skipped themselves; restore the all-zero tile counters.
         CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
         return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
+    }
+    {   // capacity hint for the fast path of the next render with this tile configuration
+        const unsigned long long longest = ctx->counters_host[1];
+        const unsigned long long want = ((longest + longest / 4 + 32) + 31) / 32 * 32;
+        ctx->bin_cap_hint[n_tiles] = (want * n_tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
     }
     if (ctx->counters_host[3] & 2ull) {
         if (pairs > 0xfffffff0ull) {

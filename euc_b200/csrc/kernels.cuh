@@ -82,6 +82,7 @@ struct Params {
     uint2* tile_range;      // (offset, n) per tile
     uint32_t* tile_list;
     uint32_t list_capacity;
+    uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
     int32_t stats;
     SamplerDev samp[EUC_MAX_SAMPLERS];
@@ -303,7 +304,19 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
     TileRect r;
     bool valid = live && tile_rect(p, bbox, layer, r);
     uint32_t npairs = 0;
-    for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
+    if (p.bin_cap) {
+        // fast path: every tile owns bin_cap slots; a tile that needs more flags the render, which is then redone on the
+        // exact count -> alloc -> fill path
+        bool over = false;
+        for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t t) {
+            const uint32_t slot = atomicAdd(p.tile_count + tile, 1u);
+            if (slot < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + slot] = t; else over = true;
+            ++npairs;
+        });
+        if (over) atomicOr(p.counters + 3, 2ull);
+    } else {
+        for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
+    }
     // total pairs (one atomic per warp)
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
@@ -325,6 +338,10 @@ __global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant_
     if (lane == 31 && total) base = atomicAdd(p.counters + 2, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (t < n_tiles) p.tile_range[t] = make_uint2((uint32_t)base + incl - n, n);
+    uint32_t mx = n;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+    if (lane == 0 && mx) atomicMax(p.counters + 1, (unsigned long long)mx);  // [1] doubles as "longest list" until raster counts fragments
     // the pair total is final here (setup has completed): flag a list that is too small for this render
     if (t == 0 && p.counters[0] > (unsigned long long)p.list_capacity) atomicOr(p.counters + 3, 2ull);
 }
@@ -560,7 +577,15 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     if (tile >= n_tiles || render_aborted(p)) return;
-    const uint2 rg = p.tile_range[tile];
+    uint2 rg;
+    if (p.bin_cap) {
+        const uint32_t cnt_t = p.tile_count[tile];
+        rg = make_uint2(tile * p.bin_cap, cnt_t);
+        __syncwarp();
+        if (lane == 0 && cnt_t) p.tile_count[tile] = 0u;  // leave the counters zeroed for the next render
+    } else {
+        rg = p.tile_range[tile];
+    }
     const uint32_t n = rg.y;
     if (n == 0) return;
     // restore submission order inside this tile's list (the fill pass appended with atomics)
