@@ -21,7 +21,7 @@ HAND_LEFT, HAND_RIGHT = range(2)
 FILTER_NEAREST, FILTER_LINEAR = range(2)
 WRAP_NONE, WRAP_CLAMP, WRAP_TILE, WRAP_MIRROR = range(4)
 TEXEL_F32, TEXEL_RGBA8_TO_F32 = range(2)
-STAGE_NAMES = ("setup", "alloc", "fill", "sort", "raster")
+STAGE_NAMES = ("setup", "alloc", "fill", "resolve", "raster")
 
 
 class SamplerDesc(C.Structure):

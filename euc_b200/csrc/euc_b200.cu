@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -43,8 +44,8 @@ struct euc_ctx {
     uint64_t next_handle = 1;
     std::unordered_map<uint64_t, Buf> bufs;
     std::unordered_map<uint64_t, Geom> geoms;
-    Scratch recs, bbox, tile_count, tile_range, tile_list, draws, uniforms, tmp_verts, tmp_idx;
-    unsigned long long* counters = nullptr;      // device, 4 words
+    Scratch recs, bbox, tile_count, tile_range, tile_list, draws, uniforms, tmp_verts, tmp_idx, winner;
+    unsigned long long* counters = nullptr;      // device, 8 words: pairs, fragments, list cursor, flags, tile ticket
     unsigned long long* counters_host = nullptr;  // pinned
     bool stats = false;
     euc_render_stats last{};
@@ -162,12 +163,35 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     const size_t smem = raster_smem_bytes<P>();
     const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
     auto kern = msaa ? raster_kernel<P, true, DEFER> : raster_kernel<P, false, DEFER>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[msaa]) {
+    static int resident[2] = {0, 0};  // CTAs of this kernel that fit one SM
+    if (!resident[msaa]) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[msaa] = true;
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, RASTER_WARPS * 32, smem));
+        resident[msaa] = std::max(nb, 1);
     }
-    auto launch_raster = [&]() { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<rblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); };
+    // persistent grid: one resident set of CTAs; warps take tiles from a ticket counter (counters[4], zeroed per render)
+    prm.static_tiles = 0u;
+    const uint32_t pblocks = std::min<uint32_t>(rblocks, (uint32_t)(ctx->sm_count * resident[msaa]));
+    const bool resolve = DEFER && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
+    if (resolve) {
+        const size_t wb = (size_t)prm.w * prm.h * prm.layers * 4;
+        if (wb > ctx->winner.cap) {  // new allocation: fill with NO_WINNER once; resolve_kernel keeps it clean afterwards
+            if ((rcode = ensure(ctx, ctx->winner, wb)) != EUC_OK) return rcode;
+            CU(cudaMemsetAsync(ctx->winner.p, 0xff, ctx->winner.cap, ctx->stream));
+        }
+        prm.winner = (uint32_t*)ctx->winner.p;
+    }
+    auto launch_raster = [&]() {
+        { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<pblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
+        if (resolve) {
+            const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
+            dim3 grid((prm.w + 31) / 32, (rows + 3) / 4, prm.layers);
+            StageTimer t(ctx, EUC_STAGE_RESOLVE);
+            if (msaa) resolve_kernel<P, true><<<grid, 128, 0, ctx->stream>>>(prm);
+            else resolve_kernel<P, false><<<grid, 128, 0, ctx->stream>>>(prm);
+        }
+    };
     auto fetch_counters = [&]() -> int {  // asynchronous copy + event; the caller waits on the event
         CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->ev_counts, ctx->stream));
@@ -188,7 +212,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         prm.tile_list = (uint32_t*)ctx->tile_list.p;
         prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
         prm.bin_cap = cap;
-        CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
         { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         if ((rcode = fetch_counters()) != EUC_OK) return rcode;
         launch_raster();
@@ -216,7 +240,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     prm.tile_list = (uint32_t*)ctx->tile_list.p;
     prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
 
-    CU(cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     auto launch_fill_raster = [&]() {
         { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         launch_raster();
@@ -251,8 +275,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         if ((rcode = ensure(ctx, ctx->tile_list, (size_t)pairs * 4)) != EUC_OK) return rcode;
         prm.tile_list = (uint32_t*)ctx->tile_list.p;
         prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
-        unsigned long long zero = 0;
-        CU(cudaMemcpyAsync(ctx->counters + 3, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->counters + 3, 0, 2 * sizeof(unsigned long long), ctx->stream));  // flags and tile ticket
         launch_fill_raster();
         CU(cudaGetLastError());
     }
@@ -421,8 +444,8 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
     ctx->dev = device_ordinal;
     if (cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     ctx->stream = ctx->own;
-    if (cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost(&ctx->counters_host, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->counters_host, 8 * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return EUC_E_CUDA;
     }
@@ -440,7 +463,7 @@ int euc_shutdown(euc_ctx* ctx) {
     drain_profile(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
-    Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx};
+    Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
     for (Scratch* s : ss) cudaFree(s->p);
     cudaEventDestroy(ctx->ev_counts);
     cudaFree(ctx->counters);

@@ -60,6 +60,7 @@ struct Params {
     uint32_t msaa_level;
     uint32_t* pixel;
     float* depth;
+    uint32_t* winner;  // deferred pipelines: per-pixel id of the last primitive whose fragment passed (NO_WINNER = none)
     // modes (pipeline.rs:178-209)
     int32_t depth_test, depth_write, pixel_write, uses_depth;
     int32_t zclip;
@@ -82,6 +83,7 @@ struct Params {
     uint2* tile_range;      // (offset, n) per tile
     uint32_t* tile_list;
     uint32_t list_capacity;
+    uint32_t static_tiles;  // 1: warp w of CTA b walks tile 4b+w only; 0: warps take tiles from a ticket counter
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
     int32_t stats;
@@ -274,7 +276,10 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
                 for (int i = 0; i < 3; ++i) nvc = nvc && (p.zmin <= ez[i] && ez[i] <= p.zmax);
             }
             bbox = make_uint2(bx0 | (bx1 << 16), by0 | (by1 << 16));
-
+            // row-restricted renders (multi-GPU bands): primitives that miss this rank's rows are dropped here
+            const bool offband = by1 <= p.row_begin || by0 >= p.row_end || bx1 <= bx0 || by1 <= by0;
+            if (offband) bbox = make_uint2(0u, 0u);
+            if (!offband) {
             float4* r4 = reinterpret_cast<float4*>(rec);
             r4[0] = make_float4(o[0], o[1], o[2], wdx[0]);
             r4[1] = make_float4(wdx[1], wdx[2], wdy[0], wdy[1]);
@@ -294,6 +299,7 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
                     for (int k = 0; k < P::V; ++k) flat[i * P::V + k] = (i == 1) ? var[1][k] : ((i == 0) != rev ? var[0][k] : var[2][k]);
 #pragma unroll
                 for (int k = 0; k < L::VPAD / 4; ++k) r4[6 + k] = make_float4(flat[4 * k], flat[4 * k + 1], flat[4 * k + 2], flat[4 * k + 3]);
+            }
             }
         }
         p.tri_bbox[tri] = bbox;
@@ -558,25 +564,16 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
     }
 }
 
+// One 16x16 tile, walked by one warp.
+// Not inlined on purpose: inside the persistent loop the register allocation of the (large) tile body got worse.
+// Returns (mbarrier phase after the tile, fragments emitted).
 template <class P, bool MSAA, bool DEFER>
-__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+__device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
+                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm) {
     using L = RecLayout<P>;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t nfrag = 0;
     constexpr uint32_t STAGE_WORDS = BATCH * L::WORDS;
-    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * 2 * STAGE_WORDS;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * 2 * STAGE_WORDS * 4) + warp * 2;
-    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (2 * STAGE_WORDS * 4 + 16)) +
-                              warp * 32 * (Q_STRIDE_WORDS + COL_STRIDE);
-    uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
-    uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
     constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
-
-    const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    if (tile >= n_tiles || render_aborted(p)) return;
     uint2 rg;
     if (p.bin_cap) {
         const uint32_t cnt_t = p.tile_count[tile];
@@ -587,7 +584,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         rg = p.tile_range[tile];
     }
     const uint32_t n = rg.y;
-    if (n == 0) return;
+    if (n == 0) return make_uint2(phase, 0u);
     // restore submission order inside this tile's list (the fill pass appended with atomics)
     // Short lists: sorted element r*32+lane ends up in register v[r] of this lane, which is exactly the id this lane
     // needs when it issues the bulk copy of batch r.  Long lists are sorted in place and read back from global memory.
@@ -686,7 +683,6 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         for (int j = 0; j < 8; ++j) col_sm[j] = cw[j];
     }
 
-    uint32_t nfrag = 0;
     // Records are processed in rounds of ROUND = 2*BATCH: both record stages are filled, then every lane walks its own
     // primitives of the round.  Longer rounds bring the busiest lane closer to the mean (the round ends when the last
     // lane is done); the load of the next round is hidden by the other warps of the SM.
@@ -701,7 +697,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         __syncwarp();
         if (lane < cnt0) bulk_g2s(recs_sm + lane * L::WORDS, p.recs + (size_t)id0 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
         if (lane < cnt1) bulk_g2s(recs_sm + (BATCH + lane) * L::WORDS, p.recs + (size_t)id1 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
-        mbar_wait(&bar[0], rd & 1u);
+        mbar_wait(&bar[0], phase);
+        phase ^= 1u;
         const uint32_t* stage = recs_sm;
 
         // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then per tile row the range of
@@ -901,31 +898,20 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
         }
     }
 
-    // deferred fragment + blend: once per pixel, for the last triangle that passed
+    // deferred pipelines: hand the per-pixel winners to resolve_kernel (the buffer is pre-filled with NO_WINNER)
     if (DEFER && row_ok && shade_px) {
-        uint32_t col[8];
-        if (vec_ok) {
-            const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
-            col[0] = a.x; col[1] = a.y; col[2] = a.z; col[3] = a.w; col[4] = b.x; col[5] = b.y; col[6] = b.z; col[7] = b.w;
-        } else {
+        bool any = false;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) col[j] = segx0 + j < p.w ? p.pixel[base + j] : 0u;
-        }
-        CornerCache lc, rc;
-        lc.tri = rc.tri = NO_WINNER;
+        for (int j = 0; j < 8; ++j) any = any || cw[j] != NO_WINNER;
+        if (any) {
+            if (vec_ok) {
+                *reinterpret_cast<uint4*>(p.winner + base) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                *reinterpret_cast<uint4*>(p.winner + base + 4) = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+            } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (cw[j] != NO_WINNER) {
-                const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)cw[j] * L::WORDS);
-                const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
-                float frag[4];
-                if (!MSAA) shade_at<P>(u, p.samp, rec, (float)(segx0 + j), yf, frag);
-                else msaa_fragment<P>(u, p.samp, rec, cw[j], segx0 + j, y, band_lo, p.msaa_level, lc, rc, frag);
-                col[j] = P::blend(col[j], frag);
+                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.winner[base + j] = cw[j];
             }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cw[j] = col[j];
     }
 
     if (QUEUE && row_ok && shade_px) {
@@ -947,7 +933,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
                 for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.depth[base + j] = depth[j];
             }
         }
-        if (shade_px) {
+        if (shade_px && !DEFER) {
             if (vec_ok) {
                 *reinterpret_cast<uint4*>(p.pixel + base) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
                 *reinterpret_cast<uint4*>(p.pixel + base + 4) = make_uint4(cw[4], cw[5], cw[6], cw[7]);
@@ -957,11 +943,78 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
             }
         }
     }
+    return make_uint2(phase, nfrag);
+}
+
+// Persistent kernel: every warp takes tiles from a ticket counter until none are left, so the grid is sized by the
+// machine (SMs x resident CTAs), not by the frame, and there is no partial last wave.
+template <class P, bool MSAA, bool DEFER>
+__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+    using L = RecLayout<P>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    constexpr uint32_t STAGE_WORDS = BATCH * L::WORDS;
+    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * 2 * STAGE_WORDS;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * 2 * STAGE_WORDS * 4) + warp * 2;
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (2 * STAGE_WORDS * 4 + 16)) +
+                              warp * 32 * (Q_STRIDE_WORDS + COL_STRIDE);
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
+    uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (render_aborted(p)) return;
+    uint32_t phase = 0, nfrag = 0;
+    unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
+    for (uint32_t it = 0;; ++it) {
+        uint32_t tile = 0;
+        if (p.static_tiles) {  // one tile per warp, grid sized by the frame
+            if (it) break;
+            tile = blockIdx.x * RASTER_WARPS + warp;
+        } else {
+            if (lane == 0) tile = atomicAdd(ticket, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+        }
+        if (tile >= n_tiles) break;
+        const uint2 res = raster_tile<P, MSAA, DEFER>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
+        phase = res.x;
+        nfrag += res.y;
+        __syncwarp();
+    }
     if (p.stats) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) nfrag += __shfl_xor_sync(0xffffffffu, nfrag, s);
         if (lane == 0 && nfrag) atomicAdd(p.counters + 1, (unsigned long long)nfrag);
     }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// Resolve (deferred pipelines): fragment + blend once per pixel for the winning primitive (pipeline.rs:540-577).
+// One thread per pixel, 32x4-pixel CTAs: rows of a warp are contiguous, so winner loads and colour stores coalesce,
+// and the whole GPU shades in parallel instead of one warp per tile.
+// -------------------------------------------------------------------------------------------------------
+template <class P, bool MSAA> __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Params p) {
+    using L = RecLayout<P>;
+    const uint32_t x = blockIdx.x * 32u + (threadIdx.x & 31u);
+    const uint32_t y = p.row_begin + blockIdx.y * 4u + (threadIdx.x >> 5);
+    const uint32_t layer = blockIdx.z;
+    if (x >= p.w || y >= p.h || y >= p.row_end || render_aborted(p)) return;
+    const size_t idx = (size_t)layer * p.w * p.h + (size_t)y * p.w + x;
+    const uint32_t win = p.winner[idx];
+    if (win == NO_WINNER) return;
+    p.winner[idx] = NO_WINNER;  // leave the buffer clean for the next render
+    const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)win * L::WORDS);
+    const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
+    float frag[4];
+    if (!MSAA) {
+        shade_at<P>(u, p.samp, rec, (float)x, (float)y, frag);
+    } else {
+        const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
+        CornerCache lc, rc;
+        lc.tri = rc.tri = NO_WINNER;
+        msaa_fragment<P>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
+    }
+    p.pixel[idx] = P::blend(p.pixel[idx], frag);
 }
 
 }  // namespace eucb
