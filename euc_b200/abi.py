@@ -3,6 +3,8 @@ import ctypes as C
 
 ABI_VERSION = 1
 MAX_SAMPLERS = 2
+IPC_HANDLE_BYTES = 64
+MAX_MIRRORS = 7
 
 # enum euc_status
 OK, E_INVALID, E_SIZE_MISMATCH, E_UNSUPPORTED, E_CUDA, E_OOM, E_OUT_OF_BOUNDS = 0, -1, -2, -3, -4, -5, -6
@@ -60,6 +62,7 @@ SYMBOLS = {
     "euc_buf_create": (C.c_int, [_ctx_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_buf_destroy": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_buf_clear": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p]),
+    "euc_buf_clear_rows": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
     "euc_buf_upload": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_buf_download": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_buf_device_ptr": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -74,5 +77,9 @@ SYMBOLS = {
     "euc_render": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
     "euc_render_geom": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64]),
     "euc_render_geom_rows": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "euc_buf_ipc_export": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p]),
+    "euc_buf_ipc_import": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "euc_render_geom_rows_mirrored": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                C.POINTER(C.c_uint64), C.c_uint32]),
     "euc_render_batch": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.POINTER(BatchDraw), C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]),
 }

@@ -240,6 +240,23 @@ class Buffer2d:
         v = np.array([texel], dtype=self.dtype)
         self.ctx._check(self.ctx._lib.euc_buf_clear(self.ctx._p, self.handle, v.ctypes.data_as(C.c_void_p)))
 
+    def clear_rows(self, texel, row_begin, row_end):
+        """Target::clear restricted to rows [row_begin, row_end) (row-band rendering across ranks)."""
+        v = np.array([texel], dtype=self.dtype)
+        self.ctx._check(self.ctx._lib.euc_buf_clear_rows(self.ctx._p, self.handle, v.ctypes.data_as(C.c_void_p), int(row_begin), int(row_end)))
+
+    def as_torch(self):
+        """Zero-copy torch view (int32/float32, flat) of this buffer through __cuda_array_interface__."""
+        import torch
+        ptr, nbytes = self.device_ptr()
+
+        class _CAI:
+            pass
+        o = _CAI()
+        o.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4" if self.dtype == np.float32 else "<i4",
+                                      "data": (ptr, False), "version": 3}
+        return torch.as_tensor(o, device=f"cuda:{self.ctx.device}")
+
     def upload(self, arr):
         arr = np.ascontiguousarray(arr)
         self.ctx._check(self.ctx._lib.euc_buf_upload(self.ctx._p, self.handle, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
@@ -251,6 +268,26 @@ class Buffer2d:
             out = np.empty(shape, dtype=self.dtype)
         self.ctx._check(self.ctx._lib.euc_buf_download(self.ctx._p, self.handle, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+    def ipc_export(self) -> bytes:
+        """CUDA IPC handle of this buffer (for another process on the same node)."""
+        h = C.create_string_buffer(abi.IPC_HANDLE_BYTES)
+        self.ctx._check(self.ctx._lib.euc_buf_ipc_export(self.ctx._p, self.handle, h))
+        return h.raw
+
+    @classmethod
+    def ipc_import(cls, handle: bytes, size, dtype, ctx=None, layers=1):
+        """Map a buffer exported by another process; stores into it travel over NVLink."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.dtype = np.dtype(dtype)
+        self._size = [int(size[0]), int(size[1])]
+        self.layers = int(layers)
+        out = C.c_uint64()
+        hb = C.create_string_buffer(handle, abi.IPC_HANDLE_BYTES)
+        self.ctx._check(self.ctx._lib.euc_buf_ipc_import(self.ctx._p, hb, self._size[0], self._size[1], self.layers, 4, C.byref(out)))
+        self.handle = out.value
+        return self
 
     def device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()
@@ -372,7 +409,7 @@ class Pipeline:
             d.samplers[i].format, d.samplers[i].filter, d.samplers[i].wrap = s.format, s.filter, s.wrap
         return d, keep
 
-    def render(self, vertices, pixel, depth, rows=None):
+    def render(self, vertices, pixel, depth, rows=None, mirrors=None):
         """Pipeline::render (src/pipeline.rs:248).  `vertices`: numpy vertex array (stream), IndexedVertices, or a
         device-resident Geometry.  `pixel` / `depth`: Buffer2d or Empty().  Asynchronous on the context's stream."""
         ctx = None
@@ -384,7 +421,11 @@ class Pipeline:
         d, keep = self.build_desc(lambda s: s.texture.handle)
         lib = ctx._lib
         if isinstance(vertices, Geometry):
-            if rows is None:
+            if mirrors:
+                r0, r1 = rows if rows is not None else (0, 0xFFFFFFFF)
+                arr = (C.c_uint64 * len(mirrors))(*[m.handle for m in mirrors])
+                rc = lib.euc_render_geom_rows_mirrored(ctx._p, C.byref(d), vertices.handle, pixel.handle, depth.handle, r0, r1, arr, len(mirrors))
+            elif rows is None:
                 rc = lib.euc_render_geom(ctx._p, C.byref(d), vertices.handle, pixel.handle, depth.handle)
             else:
                 rc = lib.euc_render_geom_rows(ctx._p, C.byref(d), vertices.handle, pixel.handle, depth.handle, rows[0], rows[1])

@@ -23,6 +23,7 @@ struct Buf {
     uint32_t w = 0, h = 0, layers = 0, texel = 0;
     size_t bytes = 0;
     bool owned = true;
+    bool ipc = false;  // mapped from another process (cudaIpcOpenMemHandle)
 };
 struct Geom {
     uint8_t* verts = nullptr;
@@ -140,6 +141,8 @@ struct RenderCall {
     bool batch;
     euc_buf pixel, depth;
     uint32_t row_begin, row_end;
+    const euc_buf* mirrors = nullptr;
+    uint32_t n_mirrors = 0;
 };
 
 template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
@@ -369,6 +372,15 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     prm.stats = ctx->stats ? 1 : 0;
     prm.counters = ctx->counters;
 
+    if (rc.n_mirrors > EUC_MAX_MIRRORS) return fail(ctx, EUC_E_INVALID, "at most %d mirrors", EUC_MAX_MIRRORS);
+    for (uint32_t i = 0; i < rc.n_mirrors; ++i) {
+        auto it = ctx->bufs.find(rc.mirrors[i]);
+        if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "mirror %u: unknown buffer handle", i);
+        if (!pb || it->second.w != pb->w || it->second.h != pb->h || it->second.layers != pb->layers)
+            return fail(ctx, EUC_E_SIZE_MISMATCH, "mirror %u does not have the pixel target's size", i);
+        prm.mirrors[i] = (uint32_t*)it->second.d;
+    }
+    prm.n_mirrors = prm.pixel_write ? rc.n_mirrors : 0;
     for (int i = 0; i < EUC_MAX_SAMPLERS; ++i) {
         const euc_sampler_desc& s = d.samplers[i];
         prm.samp[i] = SamplerDev{nullptr, 0, 0, s.format, s.filter, s.wrap};
@@ -459,7 +471,7 @@ int euc_shutdown(euc_ctx* ctx) {
     if (!ctx) return EUC_E_INVALID;
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->bufs) if (kv.second.owned) cudaFree(kv.second.d);
+    for (auto& kv : ctx->bufs) { if (kv.second.ipc) cudaIpcCloseMemHandle(kv.second.d); else if (kv.second.owned) cudaFree(kv.second.d); }
     drain_profile(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
@@ -557,7 +569,8 @@ int euc_buf_destroy(euc_ctx* ctx, euc_buf buf) {
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     CU(cudaStreamSynchronize(ctx->stream));
-    if (it->second.d && it->second.owned) CU(cudaFree(it->second.d));
+    if (it->second.ipc) CU(cudaIpcCloseMemHandle(it->second.d));
+    else if (it->second.d && it->second.owned) CU(cudaFree(it->second.d));
     ctx->bufs.erase(it);
     return EUC_OK;
 }
@@ -575,6 +588,28 @@ int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel) {
     const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
     ++ctx->launches;
     fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)b.d, n, v);
+    CU(cudaGetLastError());
+    return EUC_OK;
+}
+
+int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t row_begin, uint32_t row_end) {
+    if (!ctx || !texel) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    const Buf& b = it->second;
+    row_end = std::min(row_end, b.h);
+    if (row_begin >= row_end || b.w == 0) return EUC_OK;
+    uint32_t v;
+    std::memcpy(&v, texel, 4);
+    for (uint32_t l = 0; l < b.layers; ++l) {
+        uint32_t* base = (uint32_t*)b.d + ((size_t)l * b.h + row_begin) * b.w;
+        const size_t n = (size_t)(row_end - row_begin) * b.w;
+        if (((uintptr_t)base & 15u) != 0) return fail(ctx, EUC_E_UNSUPPORTED, "row range is not 16-byte aligned");
+        const size_t vec = (n + 3) / 4;
+        const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
+        ++ctx->launches;
+        fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>(base, n, v);
+    }
     CU(cudaGetLastError());
     return EUC_OK;
 }
@@ -670,6 +705,48 @@ int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom g
     const Geom& g = it->second;
     euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
     RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end};
+    return render_common(ctx, rc);
+}
+
+int euc_buf_ipc_export(euc_ctx* ctx, euc_buf buf, void* handle_out) {
+    if (!ctx || !handle_out) return EUC_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == EUC_IPC_HANDLE_BYTES, "IPC handle size");
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    if (!it->second.owned || it->second.bytes < (2u << 20))
+        return fail(ctx, EUC_E_UNSUPPORTED, "only buffers created by euc_buf_create with at least 2 MiB can be exported (allocation base == buffer base)");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, it->second.d));
+    std::memcpy(handle_out, &h, sizeof h);
+    return EUC_OK;
+}
+
+int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out) {
+    if (!ctx || !handle || !out) return EUC_E_INVALID;
+    if (texel_bytes != 4 || layers == 0) return fail(ctx, EUC_E_UNSUPPORTED, "only 4-byte texels, layers >= 1");
+    CU(cudaSetDevice(ctx->dev));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    Buf b;
+    b.d = ptr; b.w = width; b.h = height; b.layers = layers; b.texel = texel_bytes; b.owned = false; b.ipc = true;
+    b.bytes = (size_t)width * height * layers * texel_bytes;
+    uint64_t hnd = ctx->next_handle++;
+    ctx->bufs[hnd] = b;
+    *out = hnd;
+    return EUC_OK;
+}
+
+int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth, uint32_t row_begin,
+                                  uint32_t row_end, const euc_buf* mirrors, uint32_t n_mirrors) {
+    if (!ctx || !desc || (n_mirrors && !mirrors)) return EUC_E_INVALID;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    CU(cudaSetDevice(ctx->dev));
+    const Geom& g = it->second;
+    euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
+    RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end, mirrors, n_mirrors};
     return render_common(ctx, rc);
 }
 

@@ -60,6 +60,8 @@ struct Params {
     uint32_t msaa_level;
     uint32_t* pixel;
     float* depth;
+    uint32_t* mirrors[EUC_MAX_MIRRORS];  // peer framebuffers that receive this render's colour rows (fused gather)
+    uint32_t n_mirrors;
     uint32_t* winner;  // deferred pipelines: per-pixel id of the last primitive whose fragment passed (NO_WINNER = none)
     // modes (pipeline.rs:178-209)
     int32_t depth_test, depth_write, pixel_write, uses_depth;
@@ -584,7 +586,31 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         rg = p.tile_range[tile];
     }
     const uint32_t n = rg.y;
-    if (n == 0) return make_uint2(phase, 0u);
+    if (n == 0) {
+        // fused gather: a tile without primitives still owes its rows to the mirrors (immediate-mode pipelines; deferred
+        // ones forward from resolve_kernel)
+        if (p.n_mirrors && !DEFER && P::HAS_FRAGMENT && p.pixel_write) {
+            const uint32_t tpl = p.tiles_x * p.tiles_y, lay = tile / tpl, tl0 = tile - lay * tpl;
+            const uint32_t ty0 = tl0 / p.tiles_x, tx0 = tl0 - ty0 * p.tiles_x;
+            const uint32_t yy = ty0 * TILE + (lane >> 1), sx = tx0 * TILE + (lane & 1u) * 8u;
+            if (yy < p.h && yy >= p.row_begin && yy < p.row_end && sx < p.w) {
+                const size_t bs = (size_t)lay * p.w * p.h + (size_t)yy * p.w + sx;
+                if (sx + 8u <= p.w && (p.w & 3u) == 0) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + bs), b2 = *reinterpret_cast<const uint4*>(p.pixel + bs + 4);
+                    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) {
+                        *reinterpret_cast<uint4*>(p.mirrors[mi] + bs) = a;
+                        *reinterpret_cast<uint4*>(p.mirrors[mi] + bs + 4) = b2;
+                    }
+                } else {
+                    for (uint32_t j = 0; j < 8u && sx + j < p.w; ++j) {
+                        const uint32_t c = p.pixel[bs + j];
+                        for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][bs + j] = c;
+                    }
+                }
+            }
+        }
+        return make_uint2(phase, 0u);
+    }
     // restore submission order inside this tile's list (the fill pass appended with atomics)
     // Short lists: sorted element r*32+lane ends up in register v[r] of this lane, which is exactly the id this lane
     // needs when it issues the bulk copy of batch r.  Long lists are sorted in place and read back from global memory.
@@ -935,11 +961,21 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         }
         if (shade_px && !DEFER) {
             if (vec_ok) {
-                *reinterpret_cast<uint4*>(p.pixel + base) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-                *reinterpret_cast<uint4*>(p.pixel + base + 4) = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+                const uint4 a = make_uint4(cw[0], cw[1], cw[2], cw[3]), b2 = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+                *reinterpret_cast<uint4*>(p.pixel + base) = a;
+                *reinterpret_cast<uint4*>(p.pixel + base + 4) = b2;
+                for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) {  // fused gather: peer stores over NVLink
+                    *reinterpret_cast<uint4*>(p.mirrors[mi] + base) = a;
+                    *reinterpret_cast<uint4*>(p.mirrors[mi] + base + 4) = b2;
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (segx0 + j < p.w) p.pixel[base + j] = cw[j];
+                for (int j = 0; j < 8; ++j) {
+                    if (segx0 + j < p.w) {
+                        p.pixel[base + j] = cw[j];
+                        for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][base + j] = cw[j];
+                    }
+                }
             }
         }
     }
@@ -1001,7 +1037,13 @@ template <class P, bool MSAA> __global__ void __launch_bounds__(128) resolve_ker
     if (x >= p.w || y >= p.h || y >= p.row_end || render_aborted(p)) return;
     const size_t idx = (size_t)layer * p.w * p.h + (size_t)y * p.w + x;
     const uint32_t win = p.winner[idx];
-    if (win == NO_WINNER) return;
+    if (win == NO_WINNER) {
+        if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
+            const uint32_t c = p.pixel[idx];
+            for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
+        }
+        return;
+    }
     p.winner[idx] = NO_WINNER;  // leave the buffer clean for the next render
     const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)win * L::WORDS);
     const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
@@ -1014,7 +1056,9 @@ template <class P, bool MSAA> __global__ void __launch_bounds__(128) resolve_ker
         lc.tri = rc.tri = NO_WINNER;
         msaa_fragment<P>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
     }
-    p.pixel[idx] = P::blend(p.pixel[idx], frag);
+    const uint32_t out = P::blend(p.pixel[idx], frag);
+    p.pixel[idx] = out;
+    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = out;
 }
 
 }  // namespace eucb

@@ -185,6 +185,8 @@ uint64_t euc_launch_count(euc_ctx* ctx);
 int euc_buf_create(euc_ctx* ctx, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out);
 int euc_buf_destroy(euc_ctx* ctx, euc_buf buf);
 int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel);                     /* all layers */
+/* Clear rows [row_begin, row_end) of every layer only (row-band rendering: the other rows belong to other ranks). */
+int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t row_begin, uint32_t row_end);
 int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes);       /* row-major, x + w*y, layer-major */
 int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes);           /* blocking */
 int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes);
@@ -211,6 +213,19 @@ int euc_render_geom(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, 
  * euc's row bands are independent (src/pipeline.rs:348-350). row_begin must be a multiple of 16. */
 int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth,
                          uint32_t row_begin, uint32_t row_end);
+/* Multi-GPU: export a buffer so that another process on the same node can map it (CUDA IPC), and map one. */
+#define EUC_IPC_HANDLE_BYTES 64
+int euc_buf_ipc_export(euc_ctx* ctx, euc_buf buf, void* handle_out /* EUC_IPC_HANDLE_BYTES */);
+int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes,
+                       euc_buf* out);
+/* Row-restricted render whose colour rows are ALSO stored, by the raster/resolve kernels themselves, into every
+ * `mirrors[i]` (same size and layout as `pixel`; typically peer GPUs' framebuffers mapped with euc_buf_ipc_import):
+ * the framebuffer gather is fused into the tile write-back as direct peer stores over NVLink instead of a separate
+ * collective.  Rows [row_begin,row_end) of every mirror are fully written (tiles without primitives forward the local
+ * colour).  The caller orders consumers after all ranks' renders (any stream-ordered barrier). n_mirrors <= 7. */
+#define EUC_MAX_MIRRORS 7
+int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth,
+                                  uint32_t row_begin, uint32_t row_end, const euc_buf* mirrors, uint32_t n_mirrors);
 /* n_draws independent renders in one launch sequence. `uniforms` holds n_draws blocks of
  * desc->uniform_bytes each (desc->uniforms is ignored). Draw i renders into layer draws[i].layer. */
 int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_batch_draw* draws,
