@@ -271,7 +271,18 @@ def run_ours(args, rank, world, local_rank):
                 host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
                 token = torch.zeros(1, dtype=torch.int32, device="cuda")
             depth = e.Buffer2d([w, h], np.float32, cx)
-            geom = e.Geometry(scene["verts"], scene["idx"], cx)
+            if world > 1:
+                # geometry lives in torch tensors so that the e2e path can upload 1/world of it per rank (own PCIe link)
+                # and all-gather the rest over NVLink
+                with torch.cuda.stream(st):
+                    dv = torch.from_numpy(scene["verts"].view(np.uint8)).cuda()
+                    di = torch.from_numpy(scene["idx"].view(np.uint8)).cuda()
+                geom = e.Geometry.wrap(dv.data_ptr(), scene["verts"].dtype.itemsize, scene["verts"].shape[0], di.data_ptr(), scene["idx"].size, cx)
+                nv, ni = dv.numel() // world, di.numel() // world
+                assert nv * world == dv.numel() and ni * world == di.numel() and nv % 16 == 0 and ni % 16 == 0
+                keep.extend([dv, di])
+            else:
+                geom = e.Geometry(scene["verts"], scene["idx"], cx)
             if fused:
                 # fused gather: every rank's raster kernel stores its colour rows into all peers' framebuffers (CUDA IPC
                 # mappings, NVLink); a 4-byte all-reduce is the only collective (completion barrier)
@@ -303,12 +314,21 @@ def run_ours(args, rank, world, local_rank):
                         dist.all_gather_into_tensor(gather, my_slot)
 
             def frame_e2e():
-                geom.update(pv.data_ptr(), pi.data_ptr())
-                frame()
-                if rank == 0:
+                if world > 1:
+                    # sharded upload: this rank's 1/world of the vertices and indices over its own PCIe link, then NVLink
+                    dv[rank * nv:(rank + 1) * nv].copy_(pv[rank * nv:(rank + 1) * nv], non_blocking=True)
+                    di[rank * ni:(rank + 1) * ni].copy_(pi[rank * ni:(rank + 1) * ni], non_blocking=True)
+                    dist.all_gather_into_tensor(dv, dv[rank * nv:(rank + 1) * nv])
+                    dist.all_gather_into_tensor(di, di[rank * ni:(rank + 1) * ni])
+                    frame()
+                    # sharded read-back: every rank returns its own rows of the frame to the host
+                    host_out[r0 * w:r1 * w].copy_(gather[r0 * w:r1 * w], non_blocking=True)
+                    if fused:
+                        dist.all_reduce(token)  # peers must not write the next frame into rows that are still being read
+                else:
+                    geom.update(pv.data_ptr(), pi.data_ptr())
+                    frame()
                     host_out.copy_(gather[: h * w], non_blocking=True)
-                if fused:
-                    dist.all_reduce(token)  # peers must not start writing the next frame into a buffer still being read
 
             return frame, frame_e2e, gather
 
@@ -334,7 +354,10 @@ def run_ours(args, rank, world, local_rank):
         config_extra = {"partition": (f"{world} row bands of {slot_rows} rows; " + ("colour rows stored into every peer framebuffer by the raster kernel (CUDA IPC / NVLink), 4-byte all-reduce as barrier"
                                       if fused else "NCCL all_gather of colour rows")) if world > 1 else "single GPU",
                         "l2": "working set (80 MB geometry + 151 MB setup records + 66 MB targets) > 126 MB L2; no flush",
-                        "e2e_pipeline": "2 frames in flight (2 contexts / streams): H2D of frame i+1 and D2H of frame i-1 overlap the kernels of frame i"}
+                        "e2e_pipeline": "2 frames in flight (2 contexts / streams): H2D of frame i+1 and D2H of frame i-1 overlap the kernels of frame i"
+                                        + ("; every rank uploads 1/N of the geometry (NCCL all-gather over NVLink completes it) and reads back its own rows" if world > 1 else "")}
+        if world > 1:
+            h2d, d2h = (pv.numel() + pi.numel()) // world * world, h * w * 4  # whole-job bytes per step, spread over the ranks
     elif wl in ("c1", "c3"):
         s, u = c["shadow"], scene["u"]
         geom = e.Geometry(scene["stream"], None, ctx)

@@ -72,6 +72,7 @@ SYMBOLS = {
     "euc_get_profile": (C.c_int, [_ctx_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_int]),
     "euc_launch_count": (C.c_uint64, [_ctx_p]),
     "euc_geom_create": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "euc_geom_wrap": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_geom_update": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "euc_geom_destroy": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_render": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),

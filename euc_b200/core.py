@@ -336,6 +336,19 @@ class Geometry:
             idx.ctypes.data_as(C.c_void_p) if idx is not None else None, self.n_indices, C.byref(h)))
         self.handle = h.value
 
+    @classmethod
+    def wrap(cls, vertices_ptr, stride, n_vertices, indices_ptr=None, n_indices=0, ctx=None):
+        """Wrap caller-owned device memory (e.g. torch tensors a collective fills) as a Geometry."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.n_vertices, self.stride, self.n_indices = int(n_vertices), int(stride), int(n_indices) if indices_ptr else 0
+        self.stream_len = self.n_indices if indices_ptr else self.n_vertices
+        h = C.c_uint64()
+        self.ctx._check(self.ctx._lib.euc_geom_wrap(self.ctx._p, C.c_void_p(int(vertices_ptr)), self.stride, self.n_vertices,
+                                                    C.c_void_p(int(indices_ptr)) if indices_ptr else None, self.n_indices, C.byref(h)))
+        self.handle = h.value
+        return self
+
     def update(self, vertices_ptr, indices_ptr=None):
         """Re-upload from host memory (raw addresses, e.g. of pinned buffers); asynchronous on the context's stream."""
         self.ctx._check(self.ctx._lib.euc_geom_update(self.ctx._p, self.handle, C.c_void_p(vertices_ptr),

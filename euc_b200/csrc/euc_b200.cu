@@ -30,6 +30,7 @@ struct Geom {
     uint32_t stride = 0, n_verts = 0;
     uint32_t* idx = nullptr;
     uint32_t n_idx = 0;
+    bool owned = true;
 };
 struct Scratch {
     void* p = nullptr;
@@ -474,7 +475,7 @@ int euc_shutdown(euc_ctx* ctx) {
     for (auto& kv : ctx->bufs) { if (kv.second.ipc) cudaIpcCloseMemHandle(kv.second.d); else if (kv.second.owned) cudaFree(kv.second.d); }
     drain_profile(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    for (auto& kv : ctx->geoms) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
+    for (auto& kv : ctx->geoms) if (kv.second.owned) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
     for (Scratch* s : ss) cudaFree(s->p);
     cudaEventDestroy(ctx->ev_counts);
@@ -672,6 +673,19 @@ int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, 
     return EUC_OK;
 }
 
+int euc_geom_wrap(euc_ctx* ctx, void* device_vertices, uint32_t vertex_stride, uint32_t n_vertices, void* device_indices, uint32_t n_indices,
+                  euc_geom* out) {
+    if (!ctx || !out || !device_vertices || vertex_stride == 0) return EUC_E_INVALID;
+    if (((uintptr_t)device_vertices & 15u) || ((uintptr_t)device_indices & 3u)) return fail(ctx, EUC_E_INVALID, "wrapped geometry must be 16-byte (vertices) / 4-byte (indices) aligned");
+    Geom g;
+    g.verts = (uint8_t*)device_vertices; g.stride = vertex_stride; g.n_verts = n_vertices;
+    g.idx = (uint32_t*)device_indices; g.n_idx = device_indices ? n_indices : 0; g.owned = false;
+    uint64_t hnd = ctx->next_handle++;
+    ctx->geoms[hnd] = g;
+    *out = hnd;
+    return EUC_OK;
+}
+
 int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uint32_t* indices) {
     if (!ctx) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
@@ -690,8 +704,10 @@ int euc_geom_destroy(euc_ctx* ctx, euc_geom geom) {
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaFree(it->second.verts));
-    if (it->second.idx) CU(cudaFree(it->second.idx));
+    if (it->second.owned) {
+        CU(cudaFree(it->second.verts));
+        if (it->second.idx) CU(cudaFree(it->second.idx));
+    }
     ctx->geoms.erase(it);
     return EUC_OK;
 }

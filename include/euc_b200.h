@@ -198,6 +198,9 @@ int euc_buf_wrap(euc_ctx* ctx, void* device_ptr, uint32_t width, uint32_t height
 /* indices may be NULL (non-indexed stream). Indices are u32 on the device (the reference uses usize). */
 int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices,
                     const uint32_t* indices, uint32_t n_indices, euc_geom* out);
+/* Wrap caller-owned device memory as a geom (e.g. buffers that a collective fills); not freed by destroy. */
+int euc_geom_wrap(euc_ctx* ctx, void* device_vertices, uint32_t vertex_stride, uint32_t n_vertices, void* device_indices,
+                  uint32_t n_indices, euc_geom* out);
 int euc_geom_destroy(euc_ctx* ctx, euc_geom geom);
 /* Re-upload vertices (and indices) into an existing geom of the same shape; asynchronous when the host memory is pinned. */
 int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uint32_t* indices);
