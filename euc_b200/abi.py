@@ -12,7 +12,7 @@ STATUS_NAMES = {0: "EUC_OK", -1: "EUC_E_INVALID", -2: "EUC_E_SIZE_MISMATCH", -3:
                 -5: "EUC_E_OOM", -6: "EUC_E_OUT_OF_BOUNDS"}
 
 # enum euc_pipeline_id
-PIPE_TEAPOT_SHADOW, PIPE_TEAPOT_PHONG, PIPE_TEX_CUBE, PIPE_BLEND_TRIS, PIPE_VOXEL_ICON, PIPE_VERTEX_COLOR = range(6)
+PIPE_TEAPOT_SHADOW, PIPE_TEAPOT_PHONG, PIPE_TEX_CUBE, PIPE_BLEND_TRIS, PIPE_VOXEL_ICON, PIPE_VERTEX_COLOR, PIPE_WIREFRAME = range(7)
 # enum euc_primitive_kind
 PRIM_TRIANGLE_LIST, PRIM_LINE_LIST, PRIM_LINE_TRIANGLE_LIST = range(3)
 # enum euc_cull_mode

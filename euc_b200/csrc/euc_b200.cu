@@ -130,6 +130,7 @@ template <class P> struct PipeInfo {
     static constexpr bool vec4_loads = true;
 };
 template <> struct PipeInfo<PipeTeapotShadow> { static constexpr bool needs_sampler = false; static constexpr int sampler_format = -1; static constexpr bool vec4_loads = false; };
+template <> struct PipeInfo<PipeWireframe> { static constexpr bool needs_sampler = false; static constexpr int sampler_format = -1; static constexpr bool vec4_loads = false; };
 template <> struct PipeInfo<PipeTeapotPhong> { static constexpr bool needs_sampler = true; static constexpr int sampler_format = EUC_TEXEL_F32; static constexpr bool vec4_loads = false; };
 template <> struct PipeInfo<PipeTexCube> { static constexpr bool needs_sampler = true; static constexpr int sampler_format = EUC_TEXEL_RGBA8_TO_F32; static constexpr bool vec4_loads = true; };
 
@@ -146,7 +147,7 @@ struct RenderCall {
     uint32_t n_mirrors = 0;
 };
 
-template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
+template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
     using L = RecLayout<P>;
     using PI = PipeInfo<P>;
     const euc_pipeline_desc& d = *rc.desc;
@@ -166,7 +167,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
     constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
     const size_t smem = raster_smem_bytes<P>();
     const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
-    auto kern = msaa ? raster_kernel<P, true, DEFER> : raster_kernel<P, false, DEFER>;
+    auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
     static int resident[2] = {0, 0};  // CTAs of this kernel that fit one SM
     if (!resident[msaa]) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -192,8 +193,8 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
             const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
             dim3 grid((prm.w + 31) / 32, (rows + 3) / 4, prm.layers);
             StageTimer t(ctx, EUC_STAGE_RESOLVE);
-            if (msaa) resolve_kernel<P, true><<<grid, 128, 0, ctx->stream>>>(prm);
-            else resolve_kernel<P, false><<<grid, 128, 0, ctx->stream>>>(prm);
+            if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
+            else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
         }
     };
     auto fetch_counters = [&]() -> int {  // asynchronous copy + event; the caller waits on the event
@@ -217,7 +218,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
         prm.bin_cap = cap;
         CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+        { StageTimer t(ctx, EUC_STAGE_SETUP); (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         if ((rcode = fetch_counters()) != EUC_OK) return rcode;
         launch_raster();
         CU(cudaGetLastError());
@@ -249,7 +250,7 @@ template <class P> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& 
         { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         launch_raster();
     };
-    { StageTimer t(ctx, EUC_STAGE_SETUP); setup_kernel<P><<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+    { StageTimer t(ctx, EUC_STAGE_SETUP); (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
     { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
     if ((rcode = fetch_counters()) != EUC_OK) return rcode;
     // counters[1] held the longest list for the host; raster accumulates the fragment count there
@@ -290,7 +291,10 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     if (!rc.desc || !rc.geom) return fail(ctx, EUC_E_INVALID, "null desc/geom");
     const euc_pipeline_desc& d = *rc.desc;
     if (d.pipeline_id < 0 || d.pipeline_id >= EUC_PIPE_COUNT) return fail(ctx, EUC_E_INVALID, "unknown pipeline_id %d", d.pipeline_id);
-    if (d.primitive_kind != EUC_PRIM_TRIANGLE_LIST) return fail(ctx, EUC_E_UNSUPPORTED, "primitive kind %d is not implemented on the device yet (TriangleList only)", d.primitive_kind);
+    if (d.primitive_kind < 0 || d.primitive_kind > EUC_PRIM_LINE_TRIANGLE_LIST) return fail(ctx, EUC_E_INVALID, "unknown primitive kind %d", d.primitive_kind);
+    const bool lines = d.primitive_kind != EUC_PRIM_TRIANGLE_LIST;
+    if (lines && d.pipeline_id != EUC_PIPE_VERTEX_COLOR && d.pipeline_id != EUC_PIPE_WIREFRAME)
+        return fail(ctx, EUC_E_UNSUPPORTED, "line primitives are built for the VERTEX_COLOR and WIREFRAME pipelines only");
     if (d.cull_mode < 0 || d.cull_mode > 2 || d.depth_test < 0 || d.depth_test > 3) return fail(ctx, EUC_E_INVALID, "bad cull/depth mode");
 
     const bool shadow = d.pipeline_id == EUC_PIPE_TEAPOT_SHADOW;
@@ -345,8 +349,11 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
         const euc_batch_draw& b = rc.draws[i];
         if ((uint64_t)b.first + b.count > stream_len) return fail(ctx, EUC_E_OUT_OF_BOUNDS, "draw %u reads past the end of the vertex stream", i);
         if (b.layer >= layers) return fail(ctx, EUC_E_INVALID, "draw %u targets layer %u of %u", i, b.layer, layers);
-        dd[i] = DrawDev{b.first, b.count, b.base_vertex, b.layer, (uint32_t)tri_total, b.count / 3};  // trailing partial primitive dropped (pipeline.rs:283)
-        tri_total += b.count / 3;
+        // primitives per draw; a trailing partial primitive is dropped (pipeline.rs:283).  LineTriangleList turns every
+        // collected triangle into three lines (primitives.rs:56-76).
+        const uint32_t nprim = d.primitive_kind == EUC_PRIM_TRIANGLE_LIST ? b.count / 3 : (d.primitive_kind == EUC_PRIM_LINE_LIST ? b.count / 2 : (b.count / 3) * 3);
+        dd[i] = DrawDev{b.first, b.count, b.base_vertex, b.layer, (uint32_t)tri_total, nprim};
+        tri_total += nprim;
     }
     if (tri_total == 0) return EUC_OK;
     if (tri_total > 0x7fffffffull) return fail(ctx, EUC_E_UNSUPPORTED, "too many primitives");
@@ -367,6 +374,7 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     }
     prm.zclip = d.z_clip_enabled != 0; prm.zmin = d.z_clip_min; prm.zmax = d.z_clip_max;
     prm.cull = d.cull_mode; prm.flip_y = d.y_axis_up ? -1.0f : 1.0f;
+    prm.prim_kind = d.primitive_kind;
     prm.vertices = rc.geom->verts; prm.vstride = rc.geom->stride; prm.n_vertices = rc.geom->n_verts;
     prm.indices = rc.geom->idx;
     prm.n_draws = rc.n_draws; prm.n_tris = (uint32_t)tri_total;
@@ -432,7 +440,8 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
         case EUC_PIPE_TEX_CUBE: rcode = render_typed<PipeTexCube>(ctx, rc, prm, n_tiles); break;
         case EUC_PIPE_BLEND_TRIS: rcode = render_typed<PipeBlendTris>(ctx, rc, prm, n_tiles); break;
         case EUC_PIPE_VOXEL_ICON: rcode = render_typed<PipeVoxelIcon>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_VERTEX_COLOR: rcode = render_typed<PipeVertexColor>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_VERTEX_COLOR: rcode = lines ? render_typed<PipeVertexColor, true>(ctx, rc, prm, n_tiles) : render_typed<PipeVertexColor>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_WIREFRAME: rcode = lines ? render_typed<PipeWireframe, true>(ctx, rc, prm, n_tiles) : render_typed<PipeWireframe>(ctx, rc, prm, n_tiles); break;
         default: rcode = EUC_E_INVALID;
     }
     // dd is pageable: make sure the async copy consumed it (render_typed synchronises; early outs do not)

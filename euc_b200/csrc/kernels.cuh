@@ -85,6 +85,7 @@ struct Params {
     uint2* tile_range;      // (offset, n) per tile
     uint32_t* tile_list;
     uint32_t list_capacity;
+    int32_t prim_kind;      // euc_primitive_kind
     uint32_t static_tiles;  // 1: warp w of CTA b walks tile 4b+w only; 0: warps take tiles from a ticket counter
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
@@ -332,6 +333,130 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
 }
 
 // -------------------------------------------------------------------------------------------------------
+// Lines (src/rasterizer/lines.rs:12-120).  The record of a line re-uses the triangle record's size and the word
+// positions of bounds / flags / draw / primitive id, so binning and list handling are shared.
+// -------------------------------------------------------------------------------------------------------
+enum : int {
+    LN_SX0 = 0, LN_SY0 = 1,  // verts_screen[0]
+    LN_NORM = 2,             // 1 / (major-axis extent in screen space)  :77-82
+    LN_EZ0 = 3, LN_EZ1 = 4,  // verts_euc[i][2]
+    LN_MINY = 5, LN_MAXY1 = 6,  // min(sy0, sy1) + 0., max(sy0, sy1) + 1.  (clamped to the band per row, :66-73)
+    LN_X1 = 8, LN_Y1 = 10, LN_X2 = 12, LN_Y2 = 14  // integer end points as i64 (:60-61)
+};
+constexpr uint32_t LN_USE_X = 1u, LN_SKIP = 2u;
+
+// `f as isize`
+__device__ __forceinline__ long long r_as_isize(float f) { return __float2ll_rz(f); }
+// f32::clamp (NaN stays NaN)
+__device__ __forceinline__ float r_clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Minor-axis offset of pixel i of the walk that clipline 0.2 performs (restated, unpinned): Bresenham with the error
+// recurrence err = 2*dminor - dmajor; if (err > 0) { minor += s; err -= 2*dmajor; } err += 2*dminor, in closed form.
+__device__ __forceinline__ long long bres_minor(long long i, long long dminor, long long dmajor) {
+    if (i == 0) return 0;
+    if ((dminor | dmajor) < (1ll << 30)) return (2 * dminor * i + dmajor - 1) / (2 * dmajor);
+    return (long long)(((__int128)2 * dminor * i + dmajor - 1) / ((__int128)2 * dmajor));
+}
+
+template <class P> __global__ void __launch_bounds__(128) setup_lines_kernel(const __grid_constant__ Params p) {
+    using L = RecLayout<P>;
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = li < p.n_tris;
+    uint2 bbox = make_uint2(0u, 0u);
+    uint32_t layer = 0;
+    bool oob = false;
+    if (live) {
+        const uint32_t d = find_draw(p, li);
+        const DrawDev dr = p.draws[d];
+        layer = dr.layer;
+        const typename P::Uniforms& u = uniforms_of<P>(p, d);
+        const uint32_t l0 = li - dr.tri_begin;
+        uint32_t s[2];
+        if (p.prim_kind == EUC_PRIM_LINE_LIST) {  // primitives.rs:89-103
+            s[0] = dr.first + 2u * l0; s[1] = s[0] + 1u;
+        } else {                                   // LineTriangleList, primitives.rs:56-76: a b, b c, c a
+            const uint32_t t = l0 / 3u, k = l0 - 3u * t;
+            s[0] = dr.first + 3u * t + k; s[1] = dr.first + 3u * t + (k + 1u) % 3u;
+        }
+        float hx[2], hy[2], hz[2], hw[2];
+        float var[2][P::V > 0 ? P::V : 1];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            long long vi = p.indices ? (long long)__ldg(p.indices + s[i]) + dr.base_vertex : (long long)s[i] + dr.base_vertex;
+            if (vi < 0 || vi >= (long long)p.n_vertices) { oob = true; vi = 0; }
+            float4 clip;
+            P::vertex(u, p.vertices + (size_t)vi * p.vstride, clip, var[i]);
+            hx[i] = clip.x * 1.0f; hy[i] = clip.y * p.flip_y; hz[i] = clip.z; hw[i] = clip.w;  // lines.rs:44
+        }
+        if (!oob) {
+            float ex[2], ey[2], ez[2], sx[2], sy[2];
+            const float size_x = (float)p.w, size_y = (float)p.h;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float w = r_max(hw[i], 0.0001f);  // :48
+                ex[i] = hx[i] / w; ey[i] = hy[i] / w; ez[i] = hz[i] / w;
+                sx[i] = size_x * (ex[i] * 0.5f + 0.5f);   // :53-54
+                sy[i] = size_y * (ey[i] * -0.5f + 0.5f);
+            }
+            const long long x1 = r_as_isize(sx[0]), y1 = r_as_isize(sy[0]), x2 = r_as_isize(sx[1]), y2 = r_as_isize(sy[1]);  // :60-61
+            const float minx = r_min(sx[0], sx[1]) + 0.0f, maxx1 = r_max(sx[0], sx[1]) + 1.0f;
+            const float miny = r_min(sy[0], sy[1]) + 0.0f, maxy1 = r_max(sy[0], sy[1]) + 1.0f;
+            // x window: the band spans the whole width (:63-64, :69-70); y bounds here are the union over all bands
+            const long long wx1 = r_as_isize(r_clampf(minx, 0.0f, size_x)), wx2 = r_as_isize(r_clampf(maxx1, 0.0f, size_x));
+            const long long wy1 = r_as_isize(r_clampf(miny, 0.0f, size_y)), wy2 = r_as_isize(r_clampf(maxy1, 0.0f, size_y));
+            // (x1 - x2).abs() > (y1 - y2).abs() with wrapping arithmetic (overflow checks are off in the reference profile)
+            auto wabs = [](long long a, long long b) { long long df = (long long)((unsigned long long)a - (unsigned long long)b); return df < 0 ? (long long)(0ull - (unsigned long long)df) : df; };
+            const bool use_x = wabs(x1, x2) > wabs(y1, y2);                          // :76
+            const float norm = 1.0f / (use_x ? sx[1] - sx[0] : sy[1] - sy[0]);      // :77-82
+            const long long LIM = 1ll << 62;
+            const bool skip = x1 <= -LIM || x1 >= LIM || x2 <= -LIM || x2 >= LIM || y1 <= -LIM || y1 >= LIM || y2 <= -LIM || y2 >= LIM;
+            const bool empty = skip || wx2 <= wx1 || wy2 <= wy1 || wy2 <= (long long)p.row_begin || wy1 >= (long long)p.row_end;
+            if (!empty) {
+                bbox = make_uint2((uint32_t)wx1 | ((uint32_t)wx2 << 16), (uint32_t)wy1 | ((uint32_t)wy2 << 16));
+                uint32_t* rec = p.recs + (size_t)li * L::WORDS;
+                float4* r4 = reinterpret_cast<float4*>(rec);
+                r4[0] = make_float4(sx[0], sy[0], norm, ez[0]);
+                r4[1] = make_float4(ez[1], miny, maxy1, 0.0f);
+                *reinterpret_cast<longlong2*>(rec + LN_X1) = make_longlong2(x1, y1);
+                *reinterpret_cast<longlong2*>(rec + LN_X2) = make_longlong2(x2, y2);
+                r4[4] = make_float4(0.0f, 0.0f, __uint_as_float(bbox.x), __uint_as_float(bbox.y));
+                r4[5] = make_float4(__uint_as_float(use_x ? LN_USE_X : 0u), __uint_as_float(d), __uint_as_float(li), 0.0f);
+                if constexpr (P::V > 0) {
+                    float flat[L::VPAD];
+#pragma unroll
+                    for (int k = 0; k < L::VPAD; ++k) flat[k] = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int k = 0; k < P::V; ++k) flat[i * P::V + k] = var[i][k];
+#pragma unroll
+                    for (int k = 0; k < L::VPAD / 4; ++k) r4[6 + k] = make_float4(flat[4 * k], flat[4 * k + 1], flat[4 * k + 2], flat[4 * k + 3]);
+                }
+            }
+        }
+        p.tri_bbox[li] = bbox;
+    }
+    if (__any_sync(0xffffffffu, oob) && oob) atomicOr(p.counters + 3, 1ull);
+    TileRect r;
+    bool valid = live && tile_rect(p, bbox, layer, r);
+    uint32_t npairs = 0;
+    if (p.bin_cap) {
+        bool over = false;
+        for_each_tile(p, valid, r, li, [&](uint32_t tile, uint32_t t) {
+            const uint32_t slot = atomicAdd(p.tile_count + tile, 1u);
+            if (slot < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + slot] = t; else over = true;
+            ++npairs;
+        });
+        if (over) atomicOr(p.counters + 3, 2ull);
+    } else {
+        for_each_tile(p, valid, r, li, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, sft);
+    if ((threadIdx.x & 31u) == 0 && npairs) atomicAdd(p.counters + 0, (unsigned long long)npairs);
+}
+
+// -------------------------------------------------------------------------------------------------------
 // K3: tile list allocation, fill, order restore
 // -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
@@ -520,10 +645,22 @@ template <class P> __device__ __forceinline__ void interpolate(const float* __re
     for (int k = 0; k < P::V; ++k) var[k] = v0[k] * w0 + v1[k] * w1 + v2[k] * w2;
 }
 
-template <class P>
+// get_v_data of a line (lines.rs:100-113): weighted_sum2(v0, v1, 1 - frac, frac) with frac along the major axis
+template <class P> __device__ __forceinline__ void interpolate_line(const float* __restrict__ rec, float xf, float yf, float* var) {
+    const bool use_x = (__float_as_uint(rec[R_FLAGS]) & LN_USE_X) != 0u;
+    const float frac = (use_x ? xf - rec[LN_SX0] : yf - rec[LN_SY0]) * rec[LN_NORM];
+    const float om = 1.0f - frac;
+    const float* v0 = rec + R_VAR;
+    const float* v1 = v0 + P::V;
+#pragma unroll
+    for (int k = 0; k < P::V; ++k) var[k] = v0[k] * om + v1[k] * frac;
+}
+
+template <class P, bool LINES = false>
 __device__ __forceinline__ void shade_at(const typename P::Uniforms& u, const SamplerDev* samp, const float* rec, float xf, float yf, float* frag) {
     float var[P::V > 0 ? P::V : 1];
-    interpolate<P>(rec, xf, yf, var);
+    if (LINES) interpolate_line<P>(rec, xf, yf, var);
+    else interpolate<P>(rec, xf, yf, var);
     P::fragment(u, samp, var, frag);
 }
 
@@ -534,7 +671,7 @@ struct CornerCache {
     uint32_t tri, cx, cy0;  // owner triangle, corner x, corner-row base of the cached column
     float t0[4], t1[4];     // fragments at (cx, cy0) and (cx, cy1)
 };
-template <class P>
+template <class P, bool LINES = false>
 __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, const SamplerDev* samp, const float* rec, uint32_t tri, uint32_t x,
                                                uint32_t y, uint32_t band_lo, uint32_t Lv, CornerCache& left, CornerCache& right, float* frag) {
     const float msaa_div = 1.0f / (float)(1u << Lv);
@@ -547,14 +684,14 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
         if (right.tri == tri && right.cx == cx0 && right.cy0 == cy0) {
             left = right;
         } else {
-            shade_at<P>(u, samp, rec, (float)cx0, (float)cy0, left.t0);
-            shade_at<P>(u, samp, rec, (float)cx0, (float)cy1, left.t1);
+            shade_at<P, LINES>(u, samp, rec, (float)cx0, (float)cy0, left.t0);
+            shade_at<P, LINES>(u, samp, rec, (float)cx0, (float)cy1, left.t1);
             left.tri = tri; left.cx = cx0; left.cy0 = cy0;
         }
     }
     if (!(right.tri == tri && right.cx == cx1 && right.cy0 == cy0)) {
-        shade_at<P>(u, samp, rec, (float)cx1, (float)cy0, right.t0);
-        shade_at<P>(u, samp, rec, (float)cx1, (float)cy1, right.t1);
+        shade_at<P, LINES>(u, samp, rec, (float)cx1, (float)cy0, right.t0);
+        shade_at<P, LINES>(u, samp, rec, (float)cx1, (float)cy1, right.t1);
         right.tri = tri; right.cx = cx1; right.cy0 = cy0;
     }
     const float omy = 1.0f - fracty, omx = 1.0f - fractx;
@@ -569,7 +706,7 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
 // One 16x16 tile, walked by one warp.
 // Not inlined on purpose: inside the persistent loop the register allocation of the (large) tile body got worse.
 // Returns (mbarrier phase after the tile, fragments emitted).
-template <class P, bool MSAA, bool DEFER>
+template <class P, bool MSAA, bool DEFER, bool LINES>
 __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
                                           uint32_t phase, uint16_t* const queue, uint32_t* const col_sm) {
     using L = RecLayout<P>;
@@ -742,6 +879,16 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
             const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
             const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
             const uint32_t ra = max(y0, tile_y0) - tile_y0, rb = min(y1, tile_y0 + TILE) - tile_y0;  // rows [ra, rb) of the tile
+            if (LINES) {
+                if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra && x1 > x0) {
+                    const uint32_t hi = rb >= 16u ? 0xffffffffu : ((1u << (2u * rb)) - 1u);
+                    const uint32_t lo = (1u << (2u * ra)) - 1u;
+                    uint32_t seg = 0;
+                    if (x0 < tile_x0 + 8u && x1 > tile_x0) seg |= 0x55555555u;
+                    if (x0 < tile_x0 + 16u && x1 > tile_x0 + 8u) seg |= 0xaaaaaaaau;
+                    m = hi & ~lo & seg;
+                }
+            } else
             if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra && x1 > x0) {
                 const bool seg0 = x0 < tile_x0 + 8u && x1 > tile_x0, seg1 = x0 < tile_x0 + 16u && x1 > tile_x0 + 8u;
                 const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
@@ -797,6 +944,67 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 if (own0) { t = (uint32_t)__ffs((int)own0) - 1u; own0 &= own0 - 1u; }
                 else { t = (uint32_t)BATCH + (uint32_t)__ffs((int)own1) - 1u; own1 &= own1 - 1u; }
                 const float4* rec4 = reinterpret_cast<const float4*>(stage + t * L::WORDS);
+                if constexpr (LINES) {
+                    const float* rec = reinterpret_cast<const float*>(rec4);
+                    const uint32_t* recu = stage + t * L::WORDS;
+                    const uint32_t wxa = recu[R_BBX] & 0xffffu, wxb = recu[R_BBX] >> 16;  // x window [wxa, wxb - 1]
+                    // y window of this row's band (lines.rs:66-67, :72-73, :86)
+                    const float blo = (float)band_lo, bhi = (float)band_hi;
+                    const long long wy1 = r_as_isize(r_clampf(rec[LN_MINY], blo, bhi)), wy2 = r_as_isize(r_clampf(rec[LN_MAXY1], blo, bhi));
+                    const long long yl = (long long)y;
+                    uint32_t passmask = 0;
+                    if (yl >= wy1 && yl <= wy2 - 1 && segx0 < wxb && segx0 + 8u > wxa) {
+                        const longlong2 pa = *reinterpret_cast<const longlong2*>(recu + LN_X1), pb = *reinterpret_cast<const longlong2*>(recu + LN_X2);
+                        const long long lx1 = pa.x, ly1 = pa.y, lx2 = pb.x, ly2 = pb.y;
+                        const long long ldx = lx2 > lx1 ? lx2 - lx1 : lx1 - lx2, ldy = ly2 > ly1 ? ly2 - ly1 : ly1 - ly2;
+                        const long long lsx = lx1 < lx2 ? 1 : -1, lsy = ly1 < ly2 ? 1 : -1;
+                        const bool xmajor = ldx >= ldy;
+                        long long xhit = 0;  // y-major: the single x of this row
+                        bool row_on = true;
+                        if (!xmajor) {
+                            const long long i = (yl - ly1) * lsy;
+                            row_on = i >= 0 && i <= ldy;
+                            if (row_on) xhit = lx1 + lsx * bres_minor(i, ldx, ldy);
+                        }
+                        const uint32_t flags = recu[R_FLAGS];
+                        const bool use_x = (flags & LN_USE_X) != 0u;
+                        const float sx0 = rec[LN_SX0], sy0 = rec[LN_SY0], norm = rec[LN_NORM], ez0 = rec[LN_EZ0], ez1 = rec[LN_EZ1];
+                        const uint32_t tri_id = recu[R_TRI];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t x = segx0 + (uint32_t)j;
+                            bool on = row_on && x >= wxa && x < wxb;
+                            if (on) {
+                                if (xmajor) {
+                                    const long long i = ((long long)x - lx1) * lsx;
+                                    on = i >= 0 && i <= ldx && ly1 + lsy * bres_minor(i, ldy, ldx) == yl;
+                                } else {
+                                    on = (long long)x == xhit;
+                                }
+                            }
+                            if (on) {
+                                const float frac = (use_x ? (float)x - sx0 : yf - sy0) * norm;   // lines.rs:90-94
+                                const float z = ez0 + frac * (ez1 - ez0);                       // :97
+                                bool pass = !p.zclip || (p.zmin <= z && z <= p.zmax);           // :99
+                                if (pass && p.depth_test != EUC_DEPTH_NONE) {
+                                    const float old_z = fast_depth ? depth[j] * dsgn : depth[j];
+                                    pass = p.depth_test == EUC_DEPTH_LESS ? (z < old_z) : (p.depth_test == EUC_DEPTH_EQUAL ? (z == old_z) : (z > old_z));
+                                }
+                                if (pass) {
+                                    passmask |= 1u << j;
+                                    if (p.depth_write) depth[j] = fast_depth ? z * dsgn : z;
+                                    if (DEFER) cw[j] = tri_id;
+                                }
+                            }
+                        }
+                    }
+                    nfrag += __popc(passmask);
+                    if (QUEUE && passmask && shade_px) {
+                        queue[qn++] = (uint16_t)((t << 8) | passmask);
+                        qf += __popc(passmask);
+                    }
+                    continue;
+                }
                 const float4 q4 = rec4[4];  // c.x c.y bbx bby
                 const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
                 const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
@@ -908,12 +1116,13 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                     float frag[4];
                     if (!MSAA) {
                         float var[P::V > 0 ? P::V : 1];
-                        interpolate_smem<P>(rec4, (float)(segx0 + j), yf, var);
+                        if (LINES) interpolate_line<P>(reinterpret_cast<const float*>(rec4), (float)(segx0 + j), yf, var);
+                        else interpolate_smem<P>(rec4, (float)(segx0 + j), yf, var);
                         P::fragment(u, p.samp, var, frag);
                     } else {
                         CornerCache lc, rc;
                         lc.tri = rc.tri = NO_WINNER;
-                        msaa_fragment<P>(u, p.samp, reinterpret_cast<const float*>(rec4), __float_as_uint(q5.z), segx0 + j, y, band_lo, p.msaa_level, lc, rc, frag);
+                        msaa_fragment<P, LINES>(u, p.samp, reinterpret_cast<const float*>(rec4), __float_as_uint(q5.z), segx0 + j, y, band_lo, p.msaa_level, lc, rc, frag);
                     }
                     col_sm[j] = P::blend(col_sm[j], frag);
                 }
@@ -984,7 +1193,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
 
 // Persistent kernel: every warp takes tiles from a ticket counter until none are left, so the grid is sized by the
 // machine (SMs x resident CTAs), not by the frame, and there is no partial last wave.
-template <class P, bool MSAA, bool DEFER>
+template <class P, bool MSAA, bool DEFER, bool LINES>
 __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
     using L = RecLayout<P>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1012,7 +1221,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
             tile = __shfl_sync(0xffffffffu, tile, 0);
         }
         if (tile >= n_tiles) break;
-        const uint2 res = raster_tile<P, MSAA, DEFER>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
+        const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
         phase = res.x;
         nfrag += res.y;
         __syncwarp();
@@ -1029,7 +1238,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
 // One thread per pixel, 32x4-pixel CTAs: rows of a warp are contiguous, so winner loads and colour stores coalesce,
 // and the whole GPU shades in parallel instead of one warp per tile.
 // -------------------------------------------------------------------------------------------------------
-template <class P, bool MSAA> __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Params p) {
+template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
     const uint32_t x = blockIdx.x * 32u + (threadIdx.x & 31u);
     const uint32_t y = p.row_begin + blockIdx.y * 4u + (threadIdx.x >> 5);
@@ -1049,12 +1258,12 @@ template <class P, bool MSAA> __global__ void __launch_bounds__(128) resolve_ker
     const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
     float frag[4];
     if (!MSAA) {
-        shade_at<P>(u, p.samp, rec, (float)x, (float)y, frag);
+        shade_at<P, LINES>(u, p.samp, rec, (float)x, (float)y, frag);
     } else {
         const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
         CornerCache lc, rc;
         lc.tri = rc.tri = NO_WINNER;
-        msaa_fragment<P>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
+        msaa_fragment<P, LINES>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
     }
     const uint32_t out = P::blend(p.pixel[idx], frag);
     p.pixel[idx] = out;

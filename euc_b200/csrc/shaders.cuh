@@ -262,4 +262,28 @@ struct PipeVertexColor {
     }
 };
 
+// examples/wireframes.rs:5-37
+struct PipeWireframe {
+    static constexpr int V = 0;
+    static constexpr bool HAS_FRAGMENT = true;
+    static constexpr bool BLEND_IGNORES_OLD = true;
+    using Uniforms = euc_uniforms_wireframe;
+    static constexpr uint32_t VERTEX_BYTES = sizeof(euc_vertex_pn);
+    static __device__ __forceinline__ void vertex(const Uniforms& u, const uint8_t* vp, float4& clip, float*) {
+        const float* f = (const float*)vp;  // :19-23
+        const float4 wpos = mat4_mul_vec4(u.m, f[0], f[1], f[2], 1.0f);
+        const float4 vw = mat4_mul_vec4(u.v, wpos.x, wpos.y, wpos.z, wpos.w);
+        clip = mat4_mul_vec4(u.p, vw.x, vw.y, vw.z, vw.w);
+    }
+    static __device__ __forceinline__ void fragment(const Uniforms&, const SamplerDev*, const float*, float* frag) {
+        frag[0] = 1.0f; frag[1] = 0.0f; frag[2] = 0.0f; frag[3] = 1.0f;  // Rgba::red()
+    }
+    static __device__ __forceinline__ uint32_t blend(uint32_t, const float* f) {  // :31-36: clamped(0,1)*255, BGRA
+        uint32_t c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float e = f[i]; e = e < 0.0f ? 0.0f : (e > 1.0f ? 1.0f : e); c[i] = r_as_u8(e * 255.0f); }
+        return pack_le(c[2], c[1], c[0], c[3]);
+    }
+};
+
 }  // namespace eucb

@@ -4,7 +4,7 @@ its fields are the uniforms, its getters fix the modes, and the shader stages ru
 import numpy as np
 
 from . import abi
-from .core import AaMode, CullMode, DepthMode, Pipeline, PixelMode
+from .core import AaMode, CullMode, DepthMode, LineList, LineTriangleList, Pipeline, PixelMode, TriangleList
 
 # vertex layouts (include/euc_b200.h)
 VERTEX_PN = np.dtype([("pos", np.float32, 3), ("normal", np.float32, 3)])                                   # 24 B
@@ -27,8 +27,10 @@ def _vec4(v):
 class _ModeMixin(Pipeline):
     """Lets tests/benches override the trait getters per instance (aa=..., depth=..., cull=..., coords=..., pixel=...)."""
 
-    def __init__(self, aa=None, depth=None, cull=None, coords=None, pixel=None):
+    def __init__(self, aa=None, depth=None, cull=None, coords=None, pixel=None, primitives=None):
         self._aa, self._depth, self._cull, self._coords, self._pixel = aa, depth, cull, coords, pixel
+        if primitives is not None:
+            self.Primitives = primitives  # type Primitives = TriangleList | LineList | LineTriangleList
 
     def aa_mode(self):
         return self._aa if self._aa is not None else super().aa_mode()
@@ -152,3 +154,17 @@ class VertexColor(_ModeMixin):
 
     def uniform_block(self):
         return _mat(self.mvp)
+
+
+class Wireframe(_ModeMixin):
+    """examples/wireframes.rs:5-37: LineTriangleList, constant red fragment, no depth, BGRA pack."""
+    pipeline_id = abi.PIPE_WIREFRAME
+    vertex_dtype = VERTEX_PN
+    Primitives = LineTriangleList
+
+    def __init__(self, m, v, p, **kw):
+        super().__init__(**kw)
+        self.m, self.v, self.p = (np.asarray(x, dtype=np.float32) for x in (m, v, p))
+
+    def uniform_block(self):
+        return _mat(self.m) + _mat(self.v) + _mat(self.p)

@@ -61,7 +61,8 @@ enum euc_pipeline_id {
     EUC_PIPE_BLEND_TRIS = 3,    /* BASELINE config 4: pre-transformed rgba triangles, src-over */
     EUC_PIPE_VOXEL_ICON = 4,    /* BASELINE config 5: lit voxel meshes, src-over               */
     EUC_PIPE_VERTEX_COLOR = 5,  /* examples/triangle.rs:7-25, examples/spinning_cube.rs:5-29   */
-    EUC_PIPE_COUNT = 6
+    EUC_PIPE_WIREFRAME = 6,     /* examples/wireframes.rs:5-37  constant-colour LineTriangleList */
+    EUC_PIPE_COUNT = 7
 };
 
 enum euc_primitive_kind { /* src/primitives.rs:21, :82, :49 */
@@ -140,6 +141,9 @@ typedef struct euc_uniforms_voxel_icon {
 
 /* EUC_PIPE_VERTEX_COLOR: vertex = euc_vertex_p4c4. */
 typedef struct euc_uniforms_vertex_color { float mvp[16]; } euc_uniforms_vertex_color;
+
+/* EUC_PIPE_WIREFRAME: vertex = euc_vertex_pn. */
+typedef struct euc_uniforms_wireframe { float m[16], v[16], p[16]; } euc_uniforms_wireframe;
 
 typedef struct euc_vertex_pn { float pos[3]; float normal[3]; } euc_vertex_pn;                     /* 24 B */
 typedef struct euc_vertex_p4uv { float pos[4]; float uv[2]; float _pad[2]; } euc_vertex_p4uv;     /* 32 B */

@@ -172,6 +172,22 @@ struct VertexColor {
     }
 };
 
+// ---- examples/wireframes.rs:5-37 -------------------------------------------------------------------------
+struct Wireframe {
+    using Vertex = euc_vertex_pn; using VertexData = Unit; using Fragment = Rgba; using Pixel = uint32_t;
+    Mat4 m, v, p;
+    std::pair<f32x4, Unit> vertex(const Vertex& vx) const {  // :19-23
+        f32x4 wpos = mat4_mul_vec4(m, {vx.pos[0], vx.pos[1], vx.pos[2], 1.0f});
+        return {mat4_mul_vec4(p, mat4_mul_vec4(v, wpos)), Unit{}};
+    }
+    Rgba fragment(Unit) const { return Rgba{{1.0f, 0.0f, 0.0f, 1.0f}}; }  // Rgba::red()
+    uint32_t blend(uint32_t, const Rgba& rgba) const {                    // :31-36, BGRA
+        uint8_t c[4];
+        for (int i = 0; i < 4; ++i) { float e = rgba[i]; e = e < 0.0f ? 0.0f : (e > 1.0f ? 1.0f : e); c[i] = f32_as_u8(e * 255.0f); }
+        return pack_le(c[2], c[1], c[0], c[3]);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // src/pipeline.rs:248-300 — Pipeline::render: target-size selection, vertex stage, primitive assembly.
 // ---------------------------------------------------------------------------------------------------------
@@ -294,6 +310,12 @@ int render_dispatch(const RenderArgs& a) {
             if (d.uniform_bytes < sizeof(euc_uniforms_vertex_color)) return EUC_E_INVALID;
             auto* u = (const euc_uniforms_vertex_color*)a.uniforms;
             VertexColor p{load_mat4(u->mvp)};
+            return render_with(p, a);
+        }
+        case EUC_PIPE_WIREFRAME: {
+            if (d.uniform_bytes < sizeof(euc_uniforms_wireframe)) return EUC_E_INVALID;
+            auto* u = (const euc_uniforms_wireframe*)a.uniforms;
+            Wireframe p{load_mat4(u->m), load_mat4(u->v), load_mat4(u->p)};
             return render_with(p, a);
         }
         default: return EUC_E_INVALID;

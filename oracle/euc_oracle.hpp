@@ -418,38 +418,41 @@ void triangles_rasterize(const std::pair<f32x4, V>* vertices, usize n_vertices, 
 // below restates its documented behaviour: Bresenham from (x1,y1) to (x2,y2) INCLUSIVE of both endpoints,
 // visiting only points inside the inclusive window, in order from the first endpoint.  (PARITY UNPINNED.)
 // ---------------------------------------------------------------------------------------------------------
+// Closed form of the walk: pixel i along the major axis (0 <= i <= dmajor) has minor offset
+// k_i = 0 for i == 0, else floor((2*dminor*i + dmajor - 1) / (2*dmajor)), i.e. the Bresenham error recurrence
+// `err = 2*dminor - dmajor; if (err > 0) { minor += s; err -= 2*dmajor; } err += 2*dminor;` (ties stay).
+// Only the pixels inside the inclusive window are visited (in walk order), so far-away end points cost nothing.
+// Segments with a coordinate beyond +-2^62 (saturated casts of garbage vertices) are skipped: their differences
+// overflow i64 and the behaviour of the real crate is unknowable here.
+inline int64_t bres_minor(int64_t i, int64_t dminor, int64_t dmajor) {
+    if (i == 0) return 0;
+    return (int64_t)(((__int128)2 * dminor * i + dmajor - 1) / ((__int128)2 * dmajor));
+}
 template <class F> inline void clipline_walk(int64_t x1, int64_t y1, int64_t x2, int64_t y2, int64_t wx1, int64_t wy1,
                                              int64_t wx2, int64_t wy2, F&& f) {
     if (wx1 > wx2 || wy1 > wy2) return;
-    int64_t dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
-    int64_t sx = x1 < x2 ? 1 : -1, sy = y1 < y2 ? 1 : -1;
-    // Guard against absurd endpoints (w <= 0 produces huge coordinates): walk is bounded by the window anyway.
-    const int64_t LIM = (int64_t)1 << 40;
-    if (dx > LIM || dy > LIM) return;
-    int64_t x = x1, y = y1;
+    const int64_t LIM = (int64_t)1 << 62;
+    if (x1 <= -LIM || x1 >= LIM || x2 <= -LIM || x2 >= LIM || y1 <= -LIM || y1 >= LIM || y2 <= -LIM || y2 >= LIM) return;
+    const __int128 dx128 = x2 > x1 ? (__int128)x2 - x1 : (__int128)x1 - x2, dy128 = y2 > y1 ? (__int128)y2 - y1 : (__int128)y1 - y2;
+    if (dx128 >= ((__int128)1 << 62) || dy128 >= ((__int128)1 << 62)) return;
+    const int64_t dx = (int64_t)dx128, dy = (int64_t)dy128;
+    const int64_t sx = x1 < x2 ? 1 : -1, sy = y1 < y2 ? 1 : -1;
     if (dx >= dy) {
-        // x-major: jump to the window in x first (exact Bresenham error update by multiplication)
-        int64_t err = 2 * dy - dx;  // decision variable after plotting first point
-        int64_t n = dx;
-        for (int64_t i = 0;; ++i) {
-            if (x >= wx1 && x <= wx2 && y >= wy1 && y <= wy2) f(x, y);
-            if (i == n) break;
-            if (err > 0) { y += sy; err -= 2 * dx; }
-            err += 2 * dy;
-            x += sx;
-            // early exit once past the window in the major direction
-            if ((sx > 0 && x > wx2) || (sx < 0 && x < wx1)) break;
+        // window columns in walk order
+        const int64_t lo = std::max(wx1, std::min(x1, x2)), hi = std::min(wx2, std::max(x1, x2));
+        for (int64_t c = 0; c <= hi - lo; ++c) {
+            const int64_t x = sx > 0 ? lo + c : hi - c;
+            const int64_t i = (x - x1) * sx;
+            const int64_t y = y1 + sy * bres_minor(i, dy, dx);
+            if (y >= wy1 && y <= wy2) f(x, y);
         }
     } else {
-        int64_t err = 2 * dx - dy;
-        int64_t n = dy;
-        for (int64_t i = 0;; ++i) {
-            if (x >= wx1 && x <= wx2 && y >= wy1 && y <= wy2) f(x, y);
-            if (i == n) break;
-            if (err > 0) { x += sx; err -= 2 * dy; }
-            err += 2 * dx;
-            y += sy;
-            if ((sy > 0 && y > wy2) || (sy < 0 && y < wy1)) break;
+        const int64_t lo = std::max(wy1, std::min(y1, y2)), hi = std::min(wy2, std::max(y1, y2));
+        for (int64_t c = 0; c <= hi - lo; ++c) {
+            const int64_t y = sy > 0 ? lo + c : hi - c;
+            const int64_t i = (y - y1) * sy;
+            const int64_t x = x1 + sx * bres_minor(i, dx, dy);
+            if (x >= wx1 && x <= wx2) f(x, y);
         }
     }
 }
