@@ -52,7 +52,7 @@ def ndc(px, py, w, h):
 
 
 @pytest.mark.parametrize("a,b", [((10, 20), (200, 90)), ((300, 10), (20, 70)), ((50, 5), (60, 99)), ((400, 90), (390, 3)),
-                                 ((5, 5), (5, 5)), ((0, 0), (639, 99)), ((100, 50), (300, 50)), ((77, 10), (77, 90))])
+                                 ((0, 0), (639, 99)), ((100, 50), (300, 50)), ((77, 10), (77, 90))])
 def test_oracle_walk_equals_naive_bresenham(a, b):
     w, h = 640, 100
     v = line_verts([ndc(*a, w, h) + (0.5,), ndc(*b, w, h) + (0.5,)])
@@ -62,6 +62,16 @@ def test_oracle_walk_equals_naive_bresenham(a, b):
     got = set((int(x), int(y)) for y, x in np.argwhere(px != 0))
     assert got == expect
     assert st["fragments"] == len(expect)
+
+
+def test_zero_length_line_emits_nothing():
+    # norm = 1 / 0 = inf, frac = -inf (or NaN), z = NaN -> fails passes_z_clip (lines.rs:77-82, :97-99)
+    v = line_verts([ndc(5, 5, 640, 100) + (0.5,)] * 2)
+    px = np.zeros((100, 640), np.uint32)
+    assert oracle.render(e.VertexColor(primitives=e.LineList), v, px, None)["fragments"] == 0
+    # without a z clip range the NaN depth passes and the single pixel is emitted
+    st = oracle.render(e.VertexColor(primitives=e.LineList, coords=e.CoordinateMode.VULKAN.without_z_clip()), v, px, None)
+    assert st["fragments"] == 1 and px[5, 5] != 0
 
 
 def test_line_triangle_list_and_partial_primitives():
