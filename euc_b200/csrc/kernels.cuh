@@ -162,11 +162,25 @@ template <class P> __device__ __forceinline__ const typename P::Uniforms& unifor
     return *reinterpret_cast<const typename P::Uniforms*>(base);
 }
 
+// Bulk (TMA, 1-D) store of a contiguous shared-memory block to global memory (SASS: UBLKCP.G.S)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // -------------------------------------------------------------------------------------------------------
 // K1 + K2: vertex shade, assemble, set up.  triangles.rs:54-173.
+// Records are written to a shared-memory stage (one slot per thread) and leave the SM as ONE bulk store per warp:
+// 32 consecutive primitives' records are contiguous in global memory, so the store is fully coalesced, whereas
+// per-thread 16-byte pieces of 144-byte records touch ~22 sectors per request.
 // -------------------------------------------------------------------------------------------------------
 template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
+    __shared__ __align__(128) uint32_t rec_stage[128][L::WORDS];
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tri < p.n_tris;
     uint2 bbox = make_uint2(0u, 0u);
@@ -218,7 +232,7 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
             t = ez[0]; ez[0] = ez[2]; ez[2] = t;
         }
 
-        uint32_t* rec = p.recs + (size_t)tri * L::WORDS;
+        uint32_t* rec = rec_stage[threadIdx.x];
         if (!culled) {
             // :86-102 coords_to_weights
             const float a0 = hx[0], a1 = hy[0], a3 = hw[0];
@@ -308,6 +322,16 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         p.tri_bbox[tri] = bbox;
     }
     if (__any_sync(0xffffffffu, oob) && oob) atomicOr(p.counters + 3, 1ull);
+    {   // one bulk store per warp: records of primitives [warp_first, warp_first + nrec)
+        const uint32_t warp_first = tri - (threadIdx.x & 31u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above, async-proxy read below
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0 && warp_first < p.n_tris) {
+            const uint32_t nrec = min(32u, p.n_tris - warp_first);
+            bulk_s2g(p.recs + (size_t)warp_first * L::WORDS, rec_stage[threadIdx.x], nrec * (uint32_t)L::BYTES);
+            bulk_commit_wait_read();  // the stage must stay intact until the copy engine has read it
+        }
+    }
 
     // per-tile population count
     TileRect r;
@@ -317,7 +341,28 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         // fast path: every tile owns bin_cap slots; a tile that needs more flags the render, which is then redone on the
         // exact count -> alloc -> fill path
         bool over = false;
-        for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t t) {
+        const uint32_t nt = valid ? r.ntx * r.nty : 0u;
+        if (valid && nt <= 8u) {
+            // small primitives: all atomics first, then all stores, so the round trips overlap instead of chaining
+            uint32_t tl[8], sl[8];
+            uint32_t jj = 0, ii = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((uint32_t)k < nt) {
+                    tl[k] = r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii;
+                    sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
+                    if (++ii == r.ntx) { ii = 0; ++jj; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((uint32_t)k < nt) {
+                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = tri; else over = true;
+                }
+            }
+            npairs += nt;
+        }
+        for_each_tile(p, valid && nt > 8u, r, tri, [&](uint32_t tile, uint32_t t) {
             const uint32_t slot = atomicAdd(p.tile_count + tile, 1u);
             if (slot < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + slot] = t; else over = true;
             ++npairs;
