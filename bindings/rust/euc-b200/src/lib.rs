@@ -1,0 +1,104 @@
+//! Safe wrappers with the call shape of `euc::Pipeline::render` (euc src/pipeline.rs:248-255) for the pipelines of
+//! euc's own bench (benches/teapot.rs).  NOT COMPILED in this repository's environment (no rustc).
+use euc_b200_sys as sys;
+use std::{cmp::Ordering, ffi::CStr, marker::PhantomData};
+
+#[derive(Debug)]
+pub struct Error { pub code: i32, pub message: String }
+
+/// One CUDA device. `Send`, not `Sync`: one host thread at a time (calls are asynchronous on the context's stream).
+pub struct Context { raw: *mut sys::euc_ctx }
+unsafe impl Send for Context {}
+
+impl Context {
+    pub fn new(device: i32) -> Result<Self, Error> {
+        let mut raw = std::ptr::null_mut();
+        let rc = unsafe { sys::euc_init(device, &mut raw) };
+        if rc != sys::EUC_OK { return Err(Error { code: rc, message: "euc_init failed: no CUDA device (there is no CPU fallback)".into() }); }
+        Ok(Self { raw })
+    }
+    fn check(&self, rc: i32) -> Result<(), Error> {
+        if rc == sys::EUC_OK { return Ok(()); }
+        let message = unsafe { CStr::from_ptr(sys::euc_last_error(self.raw)) }.to_string_lossy().into_owned();
+        Err(Error { code: rc, message })
+    }
+    pub fn sync(&self) -> Result<(), Error> { self.check(unsafe { sys::euc_sync(self.raw) }) }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { sys::euc_shutdown(self.raw); } } }
+
+/// Device-resident `Buffer2d<T>` with 4-byte texels (euc src/buffer.rs).
+pub struct Buffer2d<'c, T> { ctx: &'c Context, handle: sys::euc_buf, size: [usize; 2], _t: PhantomData<T> }
+
+impl<'c, T: Copy> Buffer2d<'c, T> {
+    /// `Buffer2d::fill(size, item)` (buffer.rs:60-67)
+    pub fn fill(ctx: &'c Context, size: [usize; 2], item: T) -> Result<Self, Error> {
+        assert_eq!(std::mem::size_of::<T>(), 4, "4-byte texels only");
+        let mut handle = 0;
+        ctx.check(unsafe { sys::euc_buf_create(ctx.raw, size[0] as u32, size[1] as u32, 1, 4, &mut handle) })?;
+        let mut b = Self { ctx, handle, size, _t: PhantomData };
+        b.clear(item)?;
+        Ok(b)
+    }
+    /// `Target::clear` (buffer.rs:213-218)
+    pub fn clear(&mut self, item: T) -> Result<(), Error> {
+        self.ctx.check(unsafe { sys::euc_buf_clear(self.ctx.raw, self.handle, &item as *const T as *const _) })
+    }
+    pub fn size(&self) -> [usize; 2] { self.size }
+    /// `Buffer::raw()` (buffer.rs:104-107): downloads (blocking)
+    pub fn raw(&self) -> Result<Vec<T>, Error> {
+        let n = self.size[0] * self.size[1];
+        let mut v = Vec::<T>::with_capacity(n);
+        self.ctx.check(unsafe { sys::euc_buf_download(self.ctx.raw, self.handle, v.as_mut_ptr() as *mut _, n * 4) })?;
+        unsafe { v.set_len(n) };
+        Ok(v)
+    }
+}
+impl<T> Drop for Buffer2d<'_, T> { fn drop(&mut self) { unsafe { sys::euc_buf_destroy(self.ctx.raw, self.handle); } } }
+
+/// `wavefront::Vertex` flattened: position + normal (include/euc_b200.h: euc_vertex_pn)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct VertexPn { pub pos: [f32; 3], pub normal: [f32; 3] }
+
+/// POD mirror of the trait getters (pipeline.rs:178-209) for a pipeline of the reference.
+fn desc_of<'r, P: euc::Pipeline<'r>>(p: &P, id: i32, uniforms: &[f32]) -> sys::euc_pipeline_desc
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    let dm = p.depth_mode();
+    let cm = p.coordinate_mode();
+    let cull: euc::CullMode = p.rasterizer_config().into();
+    sys::euc_pipeline_desc {
+        pipeline_id: id, primitive_kind: sys::EUC_PRIM_TRIANGLE_LIST,
+        cull_mode: match cull { euc::CullMode::None => 0, euc::CullMode::Back => 1, euc::CullMode::Front => 2 },
+        depth_test: match dm.test { None => 0, Some(Ordering::Less) => 1, Some(Ordering::Equal) => 2, Some(Ordering::Greater) => 3 },
+        depth_write: dm.write as i32, pixel_write: p.pixel_mode().write as i32,
+        y_axis_up: matches!(cm.y_axis_direction, euc::YAxisDirection::Up) as i32,
+        handedness: matches!(cm.handedness, euc::Handedness::Right) as i32,
+        z_clip_enabled: cm.z_clip_range.is_some() as i32,
+        z_clip_min: cm.z_clip_range.as_ref().map_or(0.0, |r| r.start),
+        z_clip_max: cm.z_clip_range.as_ref().map_or(0.0, |r| r.end),
+        msaa_level: match p.aa_mode() { euc::AaMode::Msaa { level } => level as i32, _ => 0 },
+        uniforms: uniforms.as_ptr() as *const _, uniform_bytes: (uniforms.len() * 4) as u32, _pad: 0,
+        samplers: Default::default(),
+    }
+}
+
+/// `TeapotShadow { mvp }.render(model.vertices(), &mut Empty::default(), &mut shadow)`  (benches/teapot.rs:188-192)
+pub fn render_teapot_shadow<'r, P: euc::Pipeline<'r>>(ctx: &Context, pipe: &P, mvp: vek::Mat4<f32>, vertices: &[VertexPn],
+                                                     shadow: &mut Buffer2d<f32>) -> Result<(), Error>
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    let u = mvp.into_col_array();
+    let d = desc_of(pipe, sys::EUC_PIPE_TEAPOT_SHADOW, &u);
+    ctx.check(unsafe { sys::euc_render(ctx.raw, &d, vertices.as_ptr() as *const _, 24, vertices.len() as u32,
+                                       std::ptr::null(), 0, 0 /* euc::Empty */, shadow.handle) })
+}
+
+/// `Teapot { m, v, p, light_pos, shadow: (&shadow).linear().clamped(), light_vp, cam_pos }.render(.., &mut color, &mut depth)`
+/// (benches/teapot.rs:195-204).  `uniforms` = m, v, p, light_vp (column-major), light_pos.xyz_, cam_pos.xyz_ (72 floats).
+pub fn render_teapot<'r, P: euc::Pipeline<'r>>(ctx: &Context, pipe: &P, uniforms: &[f32; 72], shadow: &Buffer2d<f32>,
+                                              vertices: &[VertexPn], color: &mut Buffer2d<u32>, depth: &mut Buffer2d<f32>) -> Result<(), Error>
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    let mut d = desc_of(pipe, sys::EUC_PIPE_TEAPOT_PHONG, uniforms);
+    d.samplers[0] = sys::euc_sampler_desc { buf: shadow.handle, format: sys::EUC_TEXEL_F32, filter: sys::EUC_FILTER_LINEAR, wrap: sys::EUC_WRAP_CLAMP, _pad: 0 };
+    ctx.check(unsafe { sys::euc_render(ctx.raw, &d, vertices.as_ptr() as *const _, 24, vertices.len() as u32,
+                                       std::ptr::null(), 0, color.handle, depth.handle) })
+}

@@ -297,3 +297,36 @@ def test_long_tile_lists_sorted():
         assert_depth_bit_exact(gz, rz, f"long list {n}")
         assert_colour_within_1lsb(gpx, rpx, f"long list {n}")
         assert gs["fragments"] == rs["fragments"] > n
+
+
+@pytest.mark.parametrize("kind", ["blend", "phong"])
+def test_mirrored_row_bands_fill_every_mirror(kind):
+    """Fused gather (euc_render_geom_rows_mirrored): two "ranks" (here: two buffers on one GPU) each render one row band
+    and mirror it into the other's framebuffer; afterwards both hold the complete frame, equal to a full render.
+    Covers the raster write-back (immediate pipelines), the resolve kernel (deferred pipelines) and empty tiles."""
+    w, h = 1280, 720
+    bands = [(0, 368), (368, 720)]
+    if kind == "blend":
+        verts, idx = scenes.blend_tris(1 << 11, w, h, seed=5)   # sparse: plenty of tiles without primitives
+        geom = e.Geometry(verts, idx)
+        make = lambda: e.BlendTris()
+        clear = 0xFF000000
+        extra = {}
+    else:
+        stream, u = scenes.teapot_stream(), scenes.teapot_uniforms(w, h, 512)
+        geom = e.Geometry(stream)
+        shadow = e.Buffer2d.fill([512, 512], 1.0)
+        e.TeapotShadow(u["shadow_mvp"]).render(geom, e.Empty(), shadow)
+        make = lambda: e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"])
+        clear = 0x00102030
+    full_c = e.Buffer2d.fill([w, h], clear, dtype=np.uint32)
+    full_z = e.Buffer2d.fill([w, h], 1.0)
+    make().render(geom, full_c, full_z)
+    cols = [e.Buffer2d.fill([w, h], 0xDEADBEEF, dtype=np.uint32) for _ in bands]   # poison: every pixel must be written
+    zs = [e.Buffer2d.fill([w, h], 1.0) for _ in bands]
+    for k, (r0, r1) in enumerate(bands):
+        cols[k].clear_rows(clear, r0, r1)
+        make().render(geom, cols[k], zs[k], rows=(r0, r1), mirrors=[cols[1 - k]])
+    want = full_c.raw()
+    for k in range(2):
+        assert np.array_equal(cols[k].raw(), want), f"buffer {k} is not the complete frame"
