@@ -191,7 +191,11 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
         { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<pblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
         if (resolve) {
             const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
-            dim3 grid((prm.w + 31) / 32, (rows + 3) / 4, prm.layers);
+            const uint32_t px_per_cta_row = msaa ? 64u : 32u;  // resolve_kernel: 2 pixels per thread with MSAA
+            const uint64_t nblocks = (uint64_t)((prm.w + px_per_cta_row - 1) / px_per_cta_row) * ((rows + 3) / 4) * prm.layers;
+            // light shaders: grid-stride over a machine-sized grid (most blocks hold no winner); heavy MSAA shading: one CTA
+            // per block so that the hardware balances the expensive blocks dynamically
+            const uint32_t grid = msaa ? (uint32_t)nblocks : (uint32_t)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 16);
             StageTimer t(ctx, EUC_STAGE_RESOLVE);
             if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
             else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);

@@ -709,6 +709,13 @@ __device__ __forceinline__ void shade_at(const typename P::Uniforms& u, const Sa
     P::fragment(u, samp, var, frag);
 }
 
+// One out-of-line copy of interpolate + fragment for the MSAA corner shades: four inlined copies of a large shader
+// (Phong with powf) per pixel made the resolve kernel instruction-cache bound (ncu: stall_no_instruction dominant).
+template <class P, bool LINES>
+__device__ __noinline__ void shade_corner(const typename P::Uniforms* u, const SamplerDev* samp, const float* rec, float xf, float yf, float* frag) {
+    shade_at<P, LINES>(*u, samp, rec, xf, yf, frag);
+}
+
 // euc's coarse-shading "MSAA" (pipeline.rs:544-570) for one pixel; corner fragments are memoised in the reference
 // (pure function of corner and primitive), so recomputing them is exact.  `cache` carries the corner pair of the
 // previous pixel group: cx0 of this group may equal cx1 of the previous one.
@@ -729,14 +736,14 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
         if (right.tri == tri && right.cx == cx0 && right.cy0 == cy0) {
             left = right;
         } else {
-            shade_at<P, LINES>(u, samp, rec, (float)cx0, (float)cy0, left.t0);
-            shade_at<P, LINES>(u, samp, rec, (float)cx0, (float)cy1, left.t1);
+            shade_corner<P, LINES>(&u, samp, rec, (float)cx0, (float)cy0, left.t0);
+            shade_corner<P, LINES>(&u, samp, rec, (float)cx0, (float)cy1, left.t1);
             left.tri = tri; left.cx = cx0; left.cy0 = cy0;
         }
     }
     if (!(right.tri == tri && right.cx == cx1 && right.cy0 == cy0)) {
-        shade_at<P, LINES>(u, samp, rec, (float)cx1, (float)cy0, right.t0);
-        shade_at<P, LINES>(u, samp, rec, (float)cx1, (float)cy1, right.t1);
+        shade_corner<P, LINES>(&u, samp, rec, (float)cx1, (float)cy0, right.t0);
+        shade_corner<P, LINES>(&u, samp, rec, (float)cx1, (float)cy1, right.t1);
         right.tri = tri; right.cx = cx1; right.cy0 = cy0;
     }
     const float omy = 1.0f - fracty, omx = 1.0f - fractx;
@@ -1283,36 +1290,54 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
 // One thread per pixel, 32x4-pixel CTAs: rows of a warp are contiguous, so winner loads and colour stores coalesce,
 // and the whole GPU shades in parallel instead of one warp per tile.
 // -------------------------------------------------------------------------------------------------------
+// PXT = pixels per thread along x: 2 with MSAA (pixels 2i and 2i+1 have the same `x >> level` for every level >= 1, so
+// they share all four shading-grid corners when they belong to the same primitive and the corner cache computes them
+// once), 1 otherwise.
 template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
-    const uint32_t x = blockIdx.x * 32u + (threadIdx.x & 31u);
-    const uint32_t y = p.row_begin + blockIdx.y * 4u + (threadIdx.x >> 5);
-    const uint32_t layer = blockIdx.z;
-    if (x >= p.w || y >= p.h || y >= p.row_end || render_aborted(p)) return;
-    const size_t idx = (size_t)layer * p.w * p.h + (size_t)y * p.w + x;
-    const uint32_t win = p.winner[idx];
-    if (win == NO_WINNER) {
-        if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
-            const uint32_t c = p.pixel[idx];
-            for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
-        }
-        return;
-    }
-    p.winner[idx] = NO_WINNER;  // leave the buffer clean for the next render
-    const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)win * L::WORDS);
-    const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
-    float frag[4];
-    if (!MSAA) {
-        shade_at<P, LINES>(u, p.samp, rec, (float)x, (float)y, frag);
-    } else {
-        const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
+    constexpr uint32_t PXT = MSAA ? 2u : 1u;
+    if (render_aborted(p)) return;
+    // grid-stride over blocks of (32*PXT) x 4 pixels: most blocks of a frame hold no winner at all, so the grid is sized
+    // by the machine and a CTA just moves on
+    const uint32_t bw = 32u * PXT, nbx = (p.w + bw - 1u) / bw;
+    const uint32_t rows = min(p.row_end, p.h) - p.row_begin, nby = (rows + 3u) / 4u;
+    const uint32_t nblocks = nbx * nby * p.layers;
+    for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const uint32_t layer = blk / (nbx * nby), b2 = blk - layer * nbx * nby, by = b2 / nbx, bx = b2 - by * nbx;
+        const uint32_t x0 = (bx * 32u + (threadIdx.x & 31u)) * PXT;
+        const uint32_t y = p.row_begin + by * 4u + (threadIdx.x >> 5);
+        if (x0 >= p.w || y >= p.h || y >= p.row_end) continue;
+        const size_t row = (size_t)layer * p.w * p.h + (size_t)y * p.w;
         CornerCache lc, rc;
         lc.tri = rc.tri = NO_WINNER;
-        msaa_fragment<P, LINES>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
+#pragma unroll
+        for (uint32_t k = 0; k < PXT; ++k) {
+            const uint32_t x = x0 + k;
+            if (x >= p.w) break;
+            const size_t idx = row + x;
+            const uint32_t win = p.winner[idx];
+            if (win == NO_WINNER) {
+                if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
+                    const uint32_t c = p.pixel[idx];
+                    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
+                }
+                continue;
+            }
+            p.winner[idx] = NO_WINNER;  // leave the buffer clean for the next render
+            const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)win * L::WORDS);
+            const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
+            float frag[4];
+            if (!MSAA) {
+                shade_at<P, LINES>(u, p.samp, rec, (float)x, (float)y, frag);
+            } else {
+                const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
+                msaa_fragment<P, LINES>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
+            }
+            const uint32_t out = P::blend(p.pixel[idx], frag);
+            p.pixel[idx] = out;
+            for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = out;
+        }
     }
-    const uint32_t out = P::blend(p.pixel[idx], frag);
-    p.pixel[idx] = out;
-    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = out;
 }
 
 }  // namespace eucb
