@@ -379,6 +379,7 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     prm.zclip = d.z_clip_enabled != 0; prm.zmin = d.z_clip_min; prm.zmax = d.z_clip_max;
     prm.cull = d.cull_mode; prm.flip_y = d.y_axis_up ? -1.0f : 1.0f;
     prm.prim_kind = d.primitive_kind;
+    prm.cta_bin = tri_total <= 65536 ? 1u : 0u;
     prm.vertices = rc.geom->verts; prm.vstride = rc.geom->stride; prm.n_vertices = rc.geom->n_verts;
     prm.indices = rc.geom->idx;
     prm.n_draws = rc.n_draws; prm.n_tris = (uint32_t)tri_total;

@@ -86,6 +86,7 @@ struct Params {
     uint32_t* tile_list;
     uint32_t list_capacity;
     int32_t prim_kind;      // euc_primitive_kind
+    uint32_t cta_bin;       // 1: primitives covering > 256 tiles are binned by the whole CTA (few, huge primitives)
     uint32_t static_tiles;  // 1: warp w of CTA b walks tile 4b+w only; 0: warps take tiles from a ticket counter
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
@@ -123,8 +124,9 @@ __device__ __forceinline__ bool tile_rect(const Params& p, uint2 bb, uint32_t la
     return true;
 }
 
-// Calls op(tile_index, tri) for every tile of every lane's rectangle.  Small rectangles are walked by their own
-// lane; large ones (more than 8 tiles) are walked by the whole warp, one triangle at a time.
+// Calls op(tile_index, tri) for every tile of every lane's rectangle.  Small rectangles (<= 8 tiles) are walked by
+// their own lane; larger ones by the whole warp, one primitive at a time; huge ones (> 256 tiles, e.g. a cube face at
+// 1080p) by the whole CTA through a shared-memory list.  Must be reached by every thread of the CTA.
 template <class OP> __device__ __forceinline__ void for_each_tile(const Params& p, bool valid, const TileRect& r, uint32_t tri, OP op) {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t nt = valid ? r.ntx * r.nty : 0u;
@@ -132,6 +134,36 @@ template <class OP> __device__ __forceinline__ void for_each_tile(const Params& 
     if (valid && small) {
         for (uint32_t j = 0; j < r.nty; ++j)
             for (uint32_t i = 0; i < r.ntx; ++i) op(r.layer_base + (r.ty0 + j) * p.tiles_x + r.tx0 + i, tri);
+    }
+    if (p.cta_bin) {  // uniform: the host enables it for renders with few primitives (barriers cost ~15 us at 2^20)
+        constexpr uint32_t HUGE_SLOTS = 32;  // per CTA; further huge primitives take the warp path below
+        __shared__ uint32_t huge_n;
+        __shared__ uint4 huge_a[HUGE_SLOTS];  // tx0, ty0, ntx, nt
+        __shared__ uint2 huge_b[HUGE_SLOTS];  // layer_base, tri
+        bool huge = valid && nt > 256u;
+        if (threadIdx.x == 0) huge_n = 0u;
+        __syncthreads();
+        if (huge) {
+            const uint32_t k = atomicAdd(&huge_n, 1u);
+            if (k < HUGE_SLOTS) {
+                huge_a[k] = make_uint4(r.tx0, r.ty0, r.ntx, nt);
+                huge_b[k] = make_uint2(r.layer_base, tri);
+            } else {
+                huge = false;
+            }
+        }
+        __syncthreads();
+        const uint32_t hn = min(huge_n, HUGE_SLOTS);
+        for (uint32_t e = 0; e < hn; ++e) {
+            const uint4 a = huge_a[e];
+            const uint2 b = huge_b[e];
+            for (uint32_t i = threadIdx.x; i < a.w; i += blockDim.x) {
+                const uint32_t j = i / a.z, k = i - j * a.z;
+                op(b.x + (a.y + j) * p.tiles_x + a.x + k, b.y);
+            }
+        }
+        __syncthreads();
+        if (huge) { valid = false; nt = 0u; }
     }
     uint32_t big = __ballot_sync(0xffffffffu, valid && !small);
     while (big) {
