@@ -165,7 +165,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
     constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
-    const size_t smem = raster_smem_bytes<P>();
+    const size_t smem = raster_smem_bytes<P, DEFER>();
     const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
     auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
     static int resident[2] = {0, 0};  // CTAs of this kernel that fit one SM

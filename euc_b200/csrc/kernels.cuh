@@ -683,8 +683,17 @@ constexpr int COL_STRIDE = 9;     // colour row of a lane: 8 words + 1 pad
 
 constexpr int IDS_REGS = 128;      // lists up to this length are sorted, and then kept, in registers (4 per lane)
 
-template <class P> constexpr size_t raster_smem_bytes() {
-    return (size_t)RASTER_WARPS * (2 * BATCH * RecLayout<P>::BYTES + 16 + 32 * (Q_STRIDE_WORDS + COL_STRIDE) * 4);
+// Shared-memory stage of the raster kernel.  Deferred pipelines only need the 24-word base of a record in the tile loop
+// (varyings are read by resolve_kernel), so only that part is copied.  A round holds 64 records when they are small
+// and 32 when they are large: the stage size decides how many CTAs fit an SM (ncu on C5: 3 CTAs/SM, issue-active 49 %).
+template <class P, bool DEFER> struct StageGeom {
+    static constexpr uint32_t REC_WORDS = DEFER ? (uint32_t)REC_BASE_WORDS : (uint32_t)RecLayout<P>::WORDS;  // words of a record kept in the stage
+    static constexpr uint32_t BATCHES = REC_WORDS * 4u <= 160u ? 2u : 1u;                                    // batches of 32 records per round
+    static constexpr uint32_t WORDS = BATCHES * BATCH * REC_WORDS;                                           // stage words per warp
+};
+
+template <class P, bool DEFER> constexpr size_t raster_smem_bytes() {
+    return (size_t)RASTER_WARPS * (StageGeom<P, DEFER>::WORDS * 4 + 16 + 32 * (Q_STRIDE_WORDS + COL_STRIDE) * 4);
 }
 
 // interpolate() reading the setup record from shared memory with 128-bit loads (lanes address different records)
@@ -795,7 +804,8 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                                           uint32_t phase, uint16_t* const queue, uint32_t* const col_sm) {
     using L = RecLayout<P>;
     uint32_t nfrag = 0;
-    constexpr uint32_t STAGE_WORDS = BATCH * L::WORDS;
+    constexpr uint32_t SW = StageGeom<P, DEFER>::REC_WORDS;
+    constexpr uint32_t NB = StageGeom<P, DEFER>::BATCHES;
     constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
     uint2 rg;
     if (p.bin_cap) {
@@ -845,7 +855,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     } else {
         uint32_t np2 = 1;
         while (np2 < n) np2 <<= 1;
-        if (np2 <= (uint32_t)SORT_SMEM && np2 <= 2u * STAGE_WORDS) {
+        if (np2 <= (uint32_t)SORT_SMEM && np2 <= StageGeom<P, DEFER>::WORDS) {
             uint32_t* a = recs_sm;  // the record stages are not in use yet
             for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? list[i] : 0xffffffffu;
             __syncwarp();
@@ -933,17 +943,17 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     // Records are processed in rounds of ROUND = 2*BATCH: both record stages are filled, then every lane walks its own
     // primitives of the round.  Longer rounds bring the busiest lane closer to the mean (the round ends when the last
     // lane is done); the load of the next round is hidden by the other warps of the SM.
-    constexpr uint32_t ROUND = 2 * BATCH;
+    constexpr uint32_t ROUND = NB * BATCH;
     const uint32_t n_rounds = (n + ROUND - 1) / ROUND;
     for (uint32_t rd = 0; rd < n_rounds; ++rd) {
         __syncwarp();  // every lane is done with the records of the previous round
         const uint32_t cnt = min(ROUND, n - rd * ROUND);
         const uint32_t cnt0 = min(cnt, (uint32_t)BATCH), cnt1 = cnt - cnt0;
-        const uint32_t id0 = batch_id(2u * rd), id1 = cnt1 ? batch_id(2u * rd + 1u) : 0u;
-        if (lane == 0) mbar_expect_tx(&bar[0], cnt * (uint32_t)L::BYTES);
+        const uint32_t id0 = batch_id(NB * rd), id1 = cnt1 ? batch_id(NB * rd + 1u) : 0u;
+        if (lane == 0) mbar_expect_tx(&bar[0], cnt * SW * 4u);
         __syncwarp();
-        if (lane < cnt0) bulk_g2s(recs_sm + lane * L::WORDS, p.recs + (size_t)id0 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
-        if (lane < cnt1) bulk_g2s(recs_sm + (BATCH + lane) * L::WORDS, p.recs + (size_t)id1 * L::WORDS, (uint32_t)L::BYTES, &bar[0]);
+        if (lane < cnt0) bulk_g2s(recs_sm + lane * SW, p.recs + (size_t)id0 * L::WORDS, SW * 4u, &bar[0]);
+        if (NB > 1 && lane < cnt1) bulk_g2s(recs_sm + (BATCH + lane) * SW, p.recs + (size_t)id1 * L::WORDS, SW * 4u, &bar[0]);
         mbar_wait(&bar[0], phase);
         phase ^= 1u;
         const uint32_t* stage = recs_sm;
@@ -958,7 +968,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         auto lane_mask = [&](uint32_t ri, bool valid) -> uint32_t {
         uint32_t m = 0;
         if (valid) {
-            const float4* rec4 = reinterpret_cast<const float4*>(stage + ri * L::WORDS);
+            const float4* rec4 = reinterpret_cast<const float4*>(stage + ri * SW);
             const float4 q4 = rec4[4];
             const uint32_t bbx = __float_as_uint(q4.z), bby = __float_as_uint(q4.w);
             const uint32_t x0 = bbx & 0xffffu, x1 = bbx >> 16, y0 = bby & 0xffffu, y1 = bby >> 16;
@@ -1018,7 +1028,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
             return row_ok ? own : 0u;
         };
         uint32_t own0 = transpose(lane_mask(lane, lane < cnt0));
-        uint32_t own1 = cnt1 ? transpose(lane_mask(BATCH + lane, lane < cnt1)) : 0u;
+        uint32_t own1 = (NB > 1 && cnt1) ? transpose(lane_mask(BATCH + lane, lane < cnt1)) : 0u;
 
         uint32_t qn = 0, qf = 0;  // queued entries / fragments of this lane
         for (;;) {
@@ -1027,10 +1037,10 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 uint32_t t;
                 if (own0) { t = (uint32_t)__ffs((int)own0) - 1u; own0 &= own0 - 1u; }
                 else { t = (uint32_t)BATCH + (uint32_t)__ffs((int)own1) - 1u; own1 &= own1 - 1u; }
-                const float4* rec4 = reinterpret_cast<const float4*>(stage + t * L::WORDS);
+                const float4* rec4 = reinterpret_cast<const float4*>(stage + t * SW);
                 if constexpr (LINES) {
                     const float* rec = reinterpret_cast<const float*>(rec4);
-                    const uint32_t* recu = stage + t * L::WORDS;
+                    const uint32_t* recu = stage + t * SW;
                     const uint32_t wxa = recu[R_BBX] & 0xffffu, wxb = recu[R_BBX] >> 16;  // x window [wxa, wxb - 1]
                     // y window of this row's band (lines.rs:66-67, :72-73, :86)
                     const float blo = (float)band_lo, bhi = (float)band_hi;
@@ -1194,7 +1204,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                     }
                     const uint32_t j = (uint32_t)__ffs((int)cur) - 1u;
                     cur &= cur - 1u;
-                    const float4* rec4 = reinterpret_cast<const float4*>(stage + ct * L::WORDS);
+                    const float4* rec4 = reinterpret_cast<const float4*>(stage + ct * SW);
                     const float4 q5 = rec4[5];
                     const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(q5.y));
                     float frag[4];
@@ -1282,10 +1292,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_
     using L = RecLayout<P>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    constexpr uint32_t STAGE_WORDS = BATCH * L::WORDS;
-    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * 2 * STAGE_WORDS;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * 2 * STAGE_WORDS * 4) + warp * 2;
-    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (2 * STAGE_WORDS * 4 + 16)) +
+    constexpr uint32_t STW = StageGeom<P, DEFER>::WORDS;
+    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * STW;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * STW * 4) + warp * 2;
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (STW * 4 + 16)) +
                               warp * 32 * (Q_STRIDE_WORDS + COL_STRIDE);
     uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
     uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
