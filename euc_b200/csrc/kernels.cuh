@@ -688,7 +688,7 @@ constexpr int IDS_REGS = 128;      // lists up to this length are sorted, and th
 // and 32 when they are large: the stage size decides how many CTAs fit an SM (ncu on C5: 3 CTAs/SM, issue-active 49 %).
 template <class P, bool DEFER> struct StageGeom {
     static constexpr uint32_t REC_WORDS = DEFER ? (uint32_t)REC_BASE_WORDS : (uint32_t)RecLayout<P>::WORDS;  // words of a record kept in the stage
-    static constexpr uint32_t BATCHES = REC_WORDS * 4u <= 160u ? 2u : 1u;                                    // batches of 32 records per round
+    static constexpr uint32_t BATCHES = REC_WORDS * 4u <= 128u ? 2u : 1u;                                    // batches of 32 records per round
     static constexpr uint32_t WORDS = BATCHES * BATCH * REC_WORDS;                                           // stage words per warp
 };
 
