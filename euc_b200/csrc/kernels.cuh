@@ -671,6 +671,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // With any depth mode that is the reference's final pixel: blend(_, fragment(last passing)) (pipeline.rs:574-576).
 // -------------------------------------------------------------------------------------------------------
 constexpr int RASTER_WARPS = 4;
+#ifndef EUC_RASTER_MIN_CTAS
+#define EUC_RASTER_MIN_CTAS 1
+#endif
 constexpr int BATCH = 32;  // setup records per bulk-copy stage (== warp size: one lane-mask per lane)
 constexpr uint32_t NO_WINNER = 0xffffffffu;
 
@@ -1288,7 +1291,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
 // Persistent kernel: every warp takes tiles from a ticket counter until none are left, so the grid is sized by the
 // machine (SMs x resident CTAs), not by the frame, and there is no partial last wave.
 template <class P, bool MSAA, bool DEFER, bool LINES>
-__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+__global__ void __launch_bounds__(RASTER_WARPS * 32, EUC_RASTER_MIN_CTAS) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
     using L = RecLayout<P>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
