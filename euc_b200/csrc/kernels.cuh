@@ -679,9 +679,15 @@ constexpr uint32_t NO_WINNER = 0xffffffffu;
 
 // Immediate-mode pipelines (blend reads the old pixel) queue passing fragments per lane and shade them with all
 // lanes in lock-step: entry = triangle-in-batch << 8 | 8-bit mask of this lane's pixels that passed.
-constexpr int Q_ENTRIES = 12;     // entries per lane (u16), lane stride 7 words -> conflict-free banks
-constexpr int Q_STRIDE_WORDS = 7;
-constexpr int Q_FRAGS = 20;       // stop generating once a lane holds this many fragments
+#ifndef EUC_Q_ENTRIES
+#define EUC_Q_ENTRIES 12
+#endif
+#ifndef EUC_Q_FRAGS
+#define EUC_Q_FRAGS 32
+#endif
+constexpr int Q_ENTRIES = EUC_Q_ENTRIES;  // entries per lane (u16); lane stride is odd in words -> conflict-free banks
+constexpr int Q_STRIDE_WORDS = (EUC_Q_ENTRIES / 2) | 1;
+constexpr int Q_FRAGS = EUC_Q_FRAGS;      // stop generating once a lane holds this many fragments
 constexpr int COL_STRIDE = 9;     // colour row of a lane: 8 words + 1 pad
 
 constexpr int IDS_REGS = 128;      // lists up to this length are sorted, and then kept, in registers (4 per lane)
