@@ -275,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
         r0, r1 = bands[rank]
         pv = torch.from_numpy(scene["verts"].view(np.uint8)).pin_memory()
         pi = torch.from_numpy(scene["idx"].view(np.uint8)).pin_memory()
-        pipe = e.BlendTris()
+        pipe = e.BlendTris().freeze()
         keep += [pv, pi]
 
         fused = world > 1 and os.environ.get("EUC_GATHER", "p2p") != "nccl"
@@ -380,8 +380,9 @@ def run_ours(args, rank, world, local_rank):
         color = e.Buffer2d([w, h], np.uint32, ctx)
         depth = e.Buffer2d([w, h], np.float32, ctx)
         aa = e.AaMode.Msaa(c["msaa"]) if c["msaa"] else None
-        p1 = e.TeapotShadow(u["shadow_mvp"])
-        p2 = e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"], aa=aa)
+        p1 = e.TeapotShadow(u["shadow_mvp"]).freeze()
+        p2 = e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"], aa=aa).freeze()
+        empty = e.Empty()
         pv = torch.from_numpy(scene["stream"].view(np.uint8)).pin_memory()
         host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
         cptr, _ = color.device_ptr()
@@ -391,7 +392,7 @@ def run_ours(args, rank, world, local_rank):
             color.clear(0)
             depth.clear(1.0)
             shadow.clear(1.0)
-            p1.render(geom, e.Empty(), shadow)
+            p1.render(geom, empty, shadow)
             if count is not None:
                 count.append(ctx.get_stats()["fragments"])
             p2.render(geom, color, depth)
@@ -407,7 +408,8 @@ def run_ours(args, rank, world, local_rank):
         geom = e.Geometry(scene["verts"], scene["idx"], ctx)
         tex = e.Buffer2d.from_array(scene["tex"], ctx)
         color = e.Buffer2d([w, h], np.uint32, ctx)
-        pipe = e.Cube(scene["mvp"], tex.linear().tiled())
+        pipe = e.Cube(scene["mvp"], tex.linear().tiled()).freeze()
+        empty = e.Empty()
         host_out = torch.empty(h * w, dtype=torch.int32).pin_memory()
         pv = torch.from_numpy(scene["verts"].view(np.uint8)).pin_memory()
         pi = torch.from_numpy(scene["idx"].view(np.uint8)).pin_memory()
@@ -415,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
 
         def frame():
             color.clear(180)
-            pipe.render(geom, color, e.Empty())
+            pipe.render(geom, color, empty)
 
         def frame_e2e():
             geom.update(pv.data_ptr(), pi.data_ptr())

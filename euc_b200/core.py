@@ -235,15 +235,20 @@ class Buffer2d:
     def size(self):
         return list(self._size)
 
+    def _texel(self, texel):
+        return C.c_float(texel) if self.dtype == np.float32 else C.c_uint32(int(texel) & 0xFFFFFFFF)
+
     def clear(self, texel):
         """Target::clear (src/buffer.rs:213-218)."""
-        v = np.array([texel], dtype=self.dtype)
-        self.ctx._check(self.ctx._lib.euc_buf_clear(self.ctx._p, self.handle, v.ctypes.data_as(C.c_void_p)))
+        rc = self.ctx._lib.euc_buf_clear(self.ctx._p, self.handle, C.byref(self._texel(texel)))
+        if rc:
+            self.ctx._check(rc)
 
     def clear_rows(self, texel, row_begin, row_end):
         """Target::clear restricted to rows [row_begin, row_end) (row-band rendering across ranks)."""
-        v = np.array([texel], dtype=self.dtype)
-        self.ctx._check(self.ctx._lib.euc_buf_clear_rows(self.ctx._p, self.handle, v.ctypes.data_as(C.c_void_p), int(row_begin), int(row_end)))
+        rc = self.ctx._lib.euc_buf_clear_rows(self.ctx._p, self.handle, C.byref(self._texel(texel)), int(row_begin), int(row_end))
+        if rc:
+            self.ctx._check(rc)
 
     def as_torch(self):
         """Zero-copy torch view (int32/float32, flat) of this buffer through __cuda_array_interface__."""
@@ -422,6 +427,12 @@ class Pipeline:
             d.samplers[i].format, d.samplers[i].filter, d.samplers[i].wrap = s.format, s.filter, s.wrap
         return d, keep
 
+    def freeze(self):
+        """Marshal the descriptor once and reuse it for every later render of this object (per-frame host overhead).
+        The pipeline's fields must not change afterwards."""
+        self._frozen = self.build_desc(lambda s: s.texture.handle)
+        return self
+
     def render(self, vertices, pixel, depth, rows=None, mirrors=None):
         """Pipeline::render (src/pipeline.rs:248).  `vertices`: numpy vertex array (stream), IndexedVertices, or a
         device-resident Geometry.  `pixel` / `depth`: Buffer2d or Empty().  Asynchronous on the context's stream."""
@@ -431,7 +442,7 @@ class Pipeline:
                 ctx = t.ctx
                 break
         ctx = ctx or default_context()
-        d, keep = self.build_desc(lambda s: s.texture.handle)
+        d, keep = getattr(self, "_frozen", None) or self.build_desc(lambda s: s.texture.handle)
         lib = ctx._lib
         if isinstance(vertices, Geometry):
             if mirrors:
@@ -452,7 +463,8 @@ class Pipeline:
             rc = lib.euc_render(ctx._p, C.byref(d), v.ctypes.data_as(C.c_void_p), v.dtype.itemsize if v.ndim == 1 else v.strides[0],
                                 v.shape[0], idx.ctypes.data_as(C.c_void_p) if idx is not None else None,
                                 0 if idx is None else idx.size, pixel.handle, depth.handle)
-        ctx._check(rc)
+        if rc:
+            ctx._check(rc)
 
     def render_batch(self, geometry, draws, uniform_blocks, pixel, depth):
         """n independent Pipeline::render calls in one launch sequence.  draws: iterable of (first, count,

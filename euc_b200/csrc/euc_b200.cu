@@ -54,7 +54,8 @@ struct euc_ctx {
     int sm_count = 148;
     uint64_t launches = 0;
     bool profiling = false;
-    cudaEvent_t ev_counts = nullptr;
+    cudaEvent_t ev_counts = nullptr, ev_setup = nullptr;
+    cudaStream_t aux = nullptr;  // counter read-back
     std::unordered_map<uint32_t, uint32_t> bin_cap_hint;  // per tile-count: bin size of the fast path (0 = use the exact path)
     std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool;
@@ -201,9 +202,14 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
             else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
         }
     };
-    auto fetch_counters = [&]() -> int {  // asynchronous copy + event; the caller waits on the event
-        CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaEventRecord(ctx->ev_counts, ctx->stream));
+    auto fetch_counters = [&]() -> int {
+        // The host needs the pair count / flags that setup (and alloc) produced.  The tiny D2H copy runs on an auxiliary
+        // stream that waits for the kernels queued so far, so the raster kernel queued next on the main stream does
+        // not sit behind the copy engine's latency.  The caller waits on ev_counts before it returns.
+        CU(cudaEventRecord(ctx->ev_setup, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_setup, 0));
+        CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->aux));
+        CU(cudaEventRecord(ctx->ev_counts, ctx->aux));
         return EUC_OK;
     };
 
@@ -257,7 +263,9 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
     { StageTimer t(ctx, EUC_STAGE_SETUP); (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
     { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
     if ((rcode = fetch_counters()) != EUC_OK) return rcode;
-    // counters[1] held the longest list for the host; raster accumulates the fragment count there
+    // counters[1] held the longest list for the host; raster accumulates the fragment count there.  The reset must
+    // follow the read-back, which runs on the auxiliary stream.
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counts, 0));
     CU(cudaMemsetAsync(ctx->counters + 1, 0, sizeof(unsigned long long), ctx->stream));
     launch_fill_raster();
     CU(cudaGetLastError());
@@ -476,7 +484,9 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
         delete ctx;
         return EUC_E_CUDA;
     }
-    if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     *out_ctx = ctx;
     return EUC_OK;
@@ -493,6 +503,8 @@ int euc_shutdown(euc_ctx* ctx) {
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
     for (Scratch* s : ss) cudaFree(s->p);
     cudaEventDestroy(ctx->ev_counts);
+    cudaEventDestroy(ctx->ev_setup);
+    cudaStreamDestroy(ctx->aux);
     cudaFree(ctx->counters);
     cudaFreeHost(ctx->counters_host);
     cudaStreamDestroy(ctx->own);
