@@ -51,6 +51,7 @@ struct euc_ctx {
     unsigned long long* counters_host = nullptr;  // pinned
     bool stats = false;
     euc_render_stats last{};
+    bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
     int sm_count = 148;
     uint64_t launches = 0;
     bool profiling = false;
@@ -189,6 +190,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
         prm.winner = (uint32_t*)ctx->winner.p;
     }
     auto launch_raster = [&]() {
+        ctx->stats_on_device = true;
         { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<pblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
         if (resolve) {
             const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
@@ -300,6 +302,8 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
 }
 
 int render_common(euc_ctx* ctx, const RenderCall& rc) {
+    ctx->last = euc_render_stats{};  // a render that returns before launching anything (quirks, empty targets) reports zeros
+    ctx->stats_on_device = false;
     if (!rc.desc || !rc.geom) return fail(ctx, EUC_E_INVALID, "null desc/geom");
     const euc_pipeline_desc& d = *rc.desc;
     if (d.pipeline_id < 0 || d.pipeline_id >= EUC_PIPE_COUNT) return fail(ctx, EUC_E_INVALID, "unknown pipeline_id %d", d.pipeline_id);
@@ -536,9 +540,11 @@ int euc_set_stats(euc_ctx* ctx, int enabled) {
 
 int euc_get_stats(euc_ctx* ctx, euc_render_stats* out) {
     if (!ctx || !out) return EUC_E_INVALID;
-    CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->last.fragments = ctx->counters_host[1];
+    if (ctx->stats_on_device) {
+        CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->last.fragments = ctx->counters_host[1];
+    }
     *out = ctx->last;
     return EUC_OK;
 }

@@ -330,3 +330,74 @@ def test_mirrored_row_bands_fill_every_mirror(kind):
     want = full_c.raw()
     for k in range(2):
         assert np.array_equal(cols[k].raw(), want), f"buffer {k} is not the complete frame"
+
+
+@pytest.mark.parametrize("level", [1, 3, 6])
+@pytest.mark.parametrize("w,h", [(640, 480), (333, 217), (2500, 600)])
+def test_msaa_immediate_mode_levels(level, w, h):
+    """euc's coarse-shading MSAA in the immediate (blending) path, including the maximum level and odd target sizes
+    (band height 20000*2^level/w changes with the level: pipeline.rs:329)."""
+    verts = _random_tris(300, 0x77 + level, size=0.35)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(aa=e.AaMode.Msaa(level)), verts, w, h, clear_px=0xFF000000)
+    assert_depth_bit_exact(gz, rz, f"msaa {level}")
+    assert_colour_within_1lsb(gpx, rpx, f"msaa {level}")
+    assert gs["fragments"] == rs["fragments"]
+    if h >= 20000 * (1 << level) // w:   # otherwise h / group_rows == 0: the reference renders nothing (pipeline.rs:330,337)
+        assert rs["fragments"] > 1000
+    else:
+        assert rs["fragments"] == 0 and (gpx == 0xFF000000).all()
+
+
+def test_msaa_vertex_color_deferred_odd_size():
+    verts = _random_tris(200, 0x99, size=0.4)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.VertexColor(aa=e.AaMode.Msaa(2), depth=e.DepthMode.LESS_WRITE, cull=e.CullMode.NONE),
+                                        verts, 1001, 333, clear_px=0)
+    assert_depth_bit_exact(gz, rz, "deferred msaa")
+    assert_colour_within_1lsb(gpx, rpx, "deferred msaa")
+
+
+def test_batch_draws_share_and_split_layers():
+    """euc_render_batch: draws 0 and 1 blend into layer 0 in submission order, draw 2 goes to layer 1, each with its own
+    uniform block and vertex range."""
+    n = 3
+    verts, idx, draws, ubs = scenes.voxel_icon_batch(n)
+    draws = [(draws[0][0], draws[0][1], draws[0][2], 0), (draws[1][0], draws[1][1], draws[1][2], 0), (draws[2][0], draws[2][1], draws[2][2], 1)]
+    geom = e.Geometry(verts, idx)
+    color = e.Buffer2d.fill([256, 256], 0, dtype=np.uint32, layers=2)
+    depth = e.Buffer2d.fill([256, 256], 1.0, layers=2)
+    # alpha-blended voxels make the order of draws 0 and 1 visible
+    e.VoxelIcon(np.eye(4), scenes.VOXEL_LIGHT_DIR, depth=e.DepthMode.NONE).render_batch(geom, draws, ubs, color, depth)
+    gpx = color.raw()
+    iv = e.IndexedVertices(idx, verts)
+    ref = np.zeros((2, 256, 256), np.uint32)
+    for k, (first, count, base, layer) in enumerate(draws):
+        oracle.render(e.VoxelIcon(scenes.voxel_icon_mvp(k), scenes.VOXEL_LIGHT_DIR, depth=e.DepthMode.NONE), iv, ref[layer], None, draw=(first, count, base))
+    for layer in range(2):
+        assert_colour_within_1lsb(gpx[layer], ref[layer], f"layer {layer}")
+    assert (ref[0] != 0).sum() > 5000
+
+
+def test_row_bands_with_msaa_equal_full_render():
+    w, h = 1280, 720
+    stream, u = scenes.teapot_stream(), scenes.teapot_uniforms(w, h, 512)
+    geom = e.Geometry(stream)
+    shadow = e.Buffer2d.fill([512, 512], 1.0)
+    e.TeapotShadow(u["shadow_mvp"]).render(geom, e.Empty(), shadow)
+    mk = lambda: e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"], aa=e.AaMode.Msaa(1))
+    full_c, full_z = e.Buffer2d.fill([w, h], 0, dtype=np.uint32), e.Buffer2d.fill([w, h], 1.0)
+    mk().render(geom, full_c, full_z)
+    part_c, part_z = e.Buffer2d.fill([w, h], 0, dtype=np.uint32), e.Buffer2d.fill([w, h], 1.0)
+    for r0, r1 in [(0, 304), (304, 512), (512, 720)]:   # cuts through euc's 31-row bands
+        mk().render(geom, part_c, part_z, rows=(r0, r1))
+    assert np.array_equal(full_c.raw(), part_c.raw())
+    assert np.array_equal(full_z.raw().view(np.uint32), part_z.raw().view(np.uint32))
+
+
+def test_depth_pass_without_write_and_pixel_only():
+    verts = _random_tris(500, 0x31, size=0.3)
+    # LESS_PASS: depth tested against a constant buffer, never written; blending sees every passing fragment in order
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(depth=e.DepthMode.LESS_PASS), verts, 640, 480, clear_px=0xFF000000, clear_z=0.6)
+    assert_depth_bit_exact(gz, rz, "LESS_PASS leaves depth alone")
+    assert (gz == np.float32(0.6)).all()
+    assert_colour_within_1lsb(gpx, rpx, "LESS_PASS")
+    assert gs["fragments"] == rs["fragments"]
