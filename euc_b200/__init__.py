@@ -8,4 +8,4 @@ from ._lib import EucError, LIB_PATH, load
 from .core import (AaMode, Buffer2d, Context, CoordinateMode, CullMode, DepthMode, Empty, Geometry, IndexedVertices,
                    LineList, LineTriangleList, Pipeline, PixelMode, Sampler, TriangleList, default_context)
 from .pipelines import (VERTEX_P4C4, VERTEX_P4UV, VERTEX_PN, VERTEX_VOXEL, BlendTris, Cube, Teapot, TeapotShadow,
-                        VertexColor, VoxelIcon, Wireframe)
+                        UserPipeline, VertexColor, VoxelIcon, Wireframe)

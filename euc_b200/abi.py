@@ -3,6 +3,7 @@ import ctypes as C
 
 ABI_VERSION = 1
 MAX_SAMPLERS = 2
+PIPE_USER_BASE = 1000
 IPC_HANDLE_BYTES = 64
 MAX_MIRRORS = 7
 
@@ -82,5 +83,7 @@ SYMBOLS = {
     "euc_buf_ipc_import": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_render_geom_rows_mirrored": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                                 C.POINTER(C.c_uint64), C.c_uint32]),
+    "euc_pipeline_register": (C.c_int, [_ctx_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]),
+    "euc_pipeline_log": (C.c_char_p, [_ctx_p]),
     "euc_render_batch": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.POINTER(BatchDraw), C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]),
 }

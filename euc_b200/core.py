@@ -151,6 +151,15 @@ class Context:
     def launch_count(self):
         return int(self._lib.euc_launch_count(self._p))
 
+    def register_pipeline(self, source: str, struct_name: str) -> int:
+        """Compile a user-written pipeline (CUDA source with the static interface of csrc/shaders.cuh) at run time with
+        NVRTC and return its pipeline id for this context.  The device analogue of `impl Pipeline for MyShader`."""
+        out = C.c_int32()
+        rc = self._lib.euc_pipeline_register(self._p, source.encode(), struct_name.encode(), C.byref(out))
+        if rc != abi.OK:
+            raise EucError(rc, self._lib.euc_last_error(self._p).decode() + "\n" + self._lib.euc_pipeline_log(self._p).decode())
+        return out.value
+
     def close(self):
         if getattr(self, "_p", None):
             self._lib.euc_shutdown(self._p)

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <array>
@@ -39,7 +40,9 @@ struct Scratch {
 
 }  // namespace
 
+struct euc_user_pipes;
 struct euc_ctx {
+    euc_user_pipes* user = nullptr;  // pipelines compiled at run time (runtime_pipeline.inc)
     int dev = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     std::string err;
@@ -149,38 +152,41 @@ struct RenderCall {
     uint32_t n_mirrors = 0;
 };
 
-template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
-    using L = RecLayout<P>;
-    using PI = PipeInfo<P>;
+// What the render driver needs from a pipeline: sizes, flags, and how to launch its kernels on ctx->stream.
+struct PipeOps {
+    uint32_t rec_bytes = 0, vertex_bytes = 0, uniform_bytes = 0;
+    bool has_fragment = false, defer = false, needs_sampler = false, vec4_loads = false;
+    int sampler_format = -1;
+    std::function<void(const Params&, uint32_t blocks)> setup;
+    std::function<void(const Params&, bool msaa, uint32_t blocks, uint32_t n_tiles)> raster;
+    std::function<void(const Params&, bool msaa, uint32_t grid)> resolve;
+    std::function<int(bool msaa)> resident;
+};
+
+// Pipeline-agnostic render driver.  `ops` describes the pipeline (record size, flags) and launches its kernels: template
+// instantiations for the built-in pipelines, NVRTC-compiled modules for pipelines registered at run time.
+int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles, const PipeOps& ops) {
     const euc_pipeline_desc& d = *rc.desc;
-    if (rc.geom->stride < P::VERTEX_BYTES || (rc.geom->stride & 3u)) return fail(ctx, EUC_E_INVALID, "vertex stride %u too small / unaligned for pipeline %d", rc.geom->stride, d.pipeline_id);
-    if (PI::vec4_loads && (rc.geom->stride & 15u)) return fail(ctx, EUC_E_INVALID, "vertex stride must be a multiple of 16 for pipeline %d", d.pipeline_id);
-    if (!std::is_same<P, PipeBlendTris>::value && d.uniform_bytes < sizeof(typename P::Uniforms)) return fail(ctx, EUC_E_INVALID, "uniform block too small (%u < %zu)", d.uniform_bytes, sizeof(typename P::Uniforms));
-    if (PI::needs_sampler && prm.pixel_write) {
+    if (rc.geom->stride < ops.vertex_bytes || (rc.geom->stride & 3u)) return fail(ctx, EUC_E_INVALID, "vertex stride %u too small / unaligned for pipeline %d", rc.geom->stride, d.pipeline_id);
+    if (ops.vec4_loads && (rc.geom->stride & 15u)) return fail(ctx, EUC_E_INVALID, "vertex stride must be a multiple of 16 for pipeline %d", d.pipeline_id);
+    if (d.uniform_bytes < ops.uniform_bytes) return fail(ctx, EUC_E_INVALID, "uniform block too small (%u < %u)", d.uniform_bytes, ops.uniform_bytes);
+    if (ops.needs_sampler && prm.pixel_write) {
         if (!prm.samp[0].data) return fail(ctx, EUC_E_INVALID, "pipeline %d needs sampler 0", d.pipeline_id);
-        if (prm.samp[0].format != PI::sampler_format) return fail(ctx, EUC_E_INVALID, "sampler 0 has the wrong texel format for pipeline %d", d.pipeline_id);
+        if (ops.sampler_format >= 0 && prm.samp[0].format != ops.sampler_format) return fail(ctx, EUC_E_INVALID, "sampler 0 has the wrong texel format for pipeline %d", d.pipeline_id);
     }
     int rcode;
-    if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * L::BYTES)) != EUC_OK) return rcode;
+    if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * ops.rec_bytes)) != EUC_OK) return rcode;
     prm.recs = (uint32_t*)ctx->recs.p;
 
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
-    constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
-    const size_t smem = raster_smem_bytes<P, DEFER>();
-    const bool msaa = prm.msaa_level > 0 && P::HAS_FRAGMENT && prm.pixel_write;
-    auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
-    static int resident[2] = {0, 0};  // CTAs of this kernel that fit one SM
-    if (!resident[msaa]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, RASTER_WARPS * 32, smem));
-        resident[msaa] = std::max(nb, 1);
-    }
+    const bool msaa = prm.msaa_level > 0 && ops.has_fragment && prm.pixel_write;
+    const int resident = ops.resident(msaa);  // CTAs of the raster kernel that fit one SM (sets its smem attribute once)
+    if (resident <= 0) return fail(ctx, EUC_E_CUDA, "raster kernel occupancy query failed");
     // persistent grid: one resident set of CTAs; warps take tiles from a ticket counter (counters[4], zeroed per render)
     prm.static_tiles = 0u;
-    const uint32_t pblocks = std::min<uint32_t>(rblocks, (uint32_t)(ctx->sm_count * resident[msaa]));
-    const bool resolve = DEFER && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
+    const uint32_t pblocks = std::min<uint32_t>(rblocks, (uint32_t)(ctx->sm_count * resident));
+    const bool resolve = ops.defer && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
     if (resolve) {
         const size_t wb = (size_t)prm.w * prm.h * prm.layers * 4;
         if (wb > ctx->winner.cap) {  // new allocation: fill with NO_WINNER once; resolve_kernel keeps it clean afterwards
@@ -191,7 +197,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
     }
     auto launch_raster = [&]() {
         ctx->stats_on_device = true;
-        { StageTimer t(ctx, EUC_STAGE_RASTER); kern<<<pblocks, RASTER_WARPS * 32, smem, ctx->stream>>>(prm, n_tiles); }
+        { StageTimer t(ctx, EUC_STAGE_RASTER); ops.raster(prm, msaa, pblocks, n_tiles); }
         if (resolve) {
             const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
             const uint32_t px_per_cta_row = msaa ? 64u : 32u;  // resolve_kernel: 2 pixels per thread with MSAA
@@ -200,8 +206,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
             // per block so that the hardware balances the expensive blocks dynamically
             const uint32_t grid = msaa ? (uint32_t)nblocks : (uint32_t)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 16);
             StageTimer t(ctx, EUC_STAGE_RESOLVE);
-            if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
-            else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
+            ops.resolve(prm, msaa, grid);
         }
     };
     auto fetch_counters = [&]() -> int {
@@ -230,7 +235,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
         prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
         prm.bin_cap = cap;
         CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        { StageTimer t(ctx, EUC_STAGE_SETUP); (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+        { StageTimer t(ctx, EUC_STAGE_SETUP); ops.setup(prm, tri_blocks); }
         if ((rcode = fetch_counters()) != EUC_OK) return rcode;
         launch_raster();
         CU(cudaGetLastError());
@@ -262,7 +267,7 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
         { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         launch_raster();
     };
-    { StageTimer t(ctx, EUC_STAGE_SETUP); (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
+    { StageTimer t(ctx, EUC_STAGE_SETUP); ops.setup(prm, tri_blocks); }
     { StageTimer t(ctx, EUC_STAGE_ALLOC); alloc_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(prm, n_tiles); }
     if ((rcode = fetch_counters()) != EUC_OK) return rcode;
     // counters[1] held the longest list for the host; raster accumulates the fragment count there.  The reset must
@@ -301,11 +306,62 @@ template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const Rend
     return EUC_OK;
 }
 
+// PipeOps of a built-in pipeline: template instantiations of the kernels.
+template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx) {
+    static thread_local PipeOps ops;
+    static thread_local euc_ctx* bound = nullptr;
+    if (bound == ctx) return ops;
+    using PI = PipeInfo<P>;
+    constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
+    ops.rec_bytes = RecLayout<P>::BYTES;
+    ops.vertex_bytes = P::VERTEX_BYTES;
+    ops.uniform_bytes = std::is_same<P, PipeBlendTris>::value ? 0u : (uint32_t)sizeof(typename P::Uniforms);
+    ops.has_fragment = P::HAS_FRAGMENT; ops.defer = DEFER;
+    ops.needs_sampler = PI::needs_sampler; ops.sampler_format = PI::sampler_format; ops.vec4_loads = PI::vec4_loads;
+    ops.setup = [ctx](const Params& prm, uint32_t blocks) { (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<blocks, 128, 0, ctx->stream>>>(prm); };
+    ops.raster = [ctx](const Params& prm, bool msaa, uint32_t blocks, uint32_t n_tiles) {
+        auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
+        kern<<<blocks, RASTER_WARPS * 32, raster_smem_bytes<P, DEFER>(), ctx->stream>>>(prm, n_tiles);
+    };
+    ops.resolve = [ctx](const Params& prm, bool msaa, uint32_t grid) {
+        if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
+        else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
+    };
+    ops.resident = [](bool msaa) -> int {
+        static int res[2] = {0, 0};
+        if (!res[msaa]) {
+            auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
+            const size_t smem = raster_smem_bytes<P, DEFER>();
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, RASTER_WARPS * 32, smem) != cudaSuccess) return -1;
+            res[msaa] = std::max(nb, 1);
+        }
+        return res[msaa];
+    };
+    bound = ctx;
+    return ops;
+}
+
+template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
+    return render_driver(ctx, rc, prm, n_tiles, builtin_ops<P, LINES>(ctx));
+}
+
+}  // namespace
+#include "runtime_pipeline.inc"
+namespace {
+
 int render_common(euc_ctx* ctx, const RenderCall& rc) {
     ctx->last = euc_render_stats{};  // a render that returns before launching anything (quirks, empty targets) reports zeros
     ctx->stats_on_device = false;
     if (!rc.desc || !rc.geom) return fail(ctx, EUC_E_INVALID, "null desc/geom");
     const euc_pipeline_desc& d = *rc.desc;
+    const UserPipe* user_pipe = nullptr;
+    if (d.pipeline_id >= EUC_PIPE_USER_BASE) {
+        if (ctx->user) { auto it = ctx->user->pipes.find(d.pipeline_id); if (it != ctx->user->pipes.end()) user_pipe = it->second; }
+        if (!user_pipe) return fail(ctx, EUC_E_INVALID, "unknown run-time pipeline id %d", d.pipeline_id);
+        if (d.primitive_kind != EUC_PRIM_TRIANGLE_LIST) return fail(ctx, EUC_E_UNSUPPORTED, "run-time pipelines support TriangleList only");
+    } else
     if (d.pipeline_id < 0 || d.pipeline_id >= EUC_PIPE_COUNT) return fail(ctx, EUC_E_INVALID, "unknown pipeline_id %d", d.pipeline_id);
     if (d.primitive_kind < 0 || d.primitive_kind > EUC_PRIM_LINE_TRIANGLE_LIST) return fail(ctx, EUC_E_INVALID, "unknown primitive kind %d", d.primitive_kind);
     const bool lines = d.primitive_kind != EUC_PRIM_TRIANGLE_LIST;
@@ -451,6 +507,7 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     prm.tile_count = (uint32_t*)ctx->tile_count.p;
     prm.tile_range = (uint2*)ctx->tile_range.p;
 
+    if (user_pipe) return render_driver(ctx, rc, prm, n_tiles, user_pipe->ops);
     switch (d.pipeline_id) {
         case EUC_PIPE_TEAPOT_SHADOW: rcode = render_typed<PipeTeapotShadow>(ctx, rc, prm, n_tiles); break;
         case EUC_PIPE_TEAPOT_PHONG: rcode = render_typed<PipeTeapotPhong>(ctx, rc, prm, n_tiles); break;
@@ -506,6 +563,10 @@ int euc_shutdown(euc_ctx* ctx) {
     for (auto& kv : ctx->geoms) if (kv.second.owned) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
     for (Scratch* s : ss) cudaFree(s->p);
+    if (ctx->user) {
+        for (auto& kv : ctx->user->pipes) { if (rt_api().ok) rt_api().ModuleUnload(kv.second->mod); delete kv.second; }
+        delete ctx->user;
+    }
     cudaEventDestroy(ctx->ev_counts);
     cudaEventDestroy(ctx->ev_setup);
     cudaStreamDestroy(ctx->aux);
@@ -797,6 +858,15 @@ int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, e
     RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end, mirrors, n_mirrors};
     return render_common(ctx, rc);
 }
+
+int euc_pipeline_register(euc_ctx* ctx, const char* source, const char* struct_name, int32_t* out_pipeline_id) {
+    if (!ctx || !source || !struct_name || !out_pipeline_id) return EUC_E_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    if (!ctx->user) ctx->user = new euc_user_pipes();
+    return register_pipeline(ctx, *ctx->user, source, struct_name, out_pipeline_id);
+}
+
+const char* euc_pipeline_log(euc_ctx* ctx) { return (ctx && ctx->user) ? ctx->user->log.c_str() : ""; }
 
 int euc_render_geom(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth) {
     return euc_render_geom_rows(ctx, desc, geom, pixel, depth, 0, 0xffffffffu);

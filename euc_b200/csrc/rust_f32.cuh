@@ -2,8 +2,10 @@
 // Every TU that includes this is compiled with --fmad=false and without -use_fast_math: rustc never contracts
 // a*b+c and euc's coverage/depth results depend on the exact rounding of every step.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 namespace eucb {
 

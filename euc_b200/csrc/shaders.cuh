@@ -3,8 +3,8 @@
 // may be contracted (TU is built with --fmad=false), the only fused operations are the explicit __fmaf_rn in
 // mat4_mul_vec4.
 #pragma once
-#include "rust_f32.cuh"
 #include "../../include/euc_b200.h"
+#include "rust_f32.cuh"
 
 namespace eucb {
 

@@ -168,3 +168,19 @@ class Wireframe(_ModeMixin):
 
     def uniform_block(self):
         return _mat(self.m) + _mat(self.v) + _mat(self.p)
+
+
+class UserPipeline(_ModeMixin):
+    """A pipeline whose shader stages were registered at run time (Context.register_pipeline).  `uniforms` is the raw
+    uniform block (bytes, laid out like the source's `Uniforms` struct); `samplers` binds up to two textures."""
+
+    def __init__(self, pipeline_id, vertex_dtype, uniforms=b"", samplers=(), **kw):
+        super().__init__(**kw)
+        self.pipeline_id, self.vertex_dtype = pipeline_id, vertex_dtype
+        self._uniforms, self._samplers = bytes(uniforms), list(samplers)
+
+    def uniform_block(self):
+        return self._uniforms
+
+    def samplers(self):
+        return self._samplers

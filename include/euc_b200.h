@@ -30,8 +30,18 @@
 #ifndef EUC_B200_H
 #define EUC_B200_H
 
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#else /* NVRTC (run-time compiled pipelines, euc_pipeline_register): no system headers */
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned long long uintptr_t;
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -233,6 +243,17 @@ int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_
 #define EUC_MAX_MIRRORS 7
 int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth,
                                   uint32_t row_begin, uint32_t row_end, const euc_buf* mirrors, uint32_t n_mirrors);
+/* Row N3 of SURVEY 8(f): pipelines whose shader stages are CUDA source compiled at run time (NVRTC), the device analogue
+ * of writing `impl Pipeline for MyShader` in the reference (src/pipeline.rs:171-244).  `source` is placed inside
+ * `namespace eucb` after the kernels of this library and must define `struct <struct_name>` with the static interface
+ * documented in euc_b200/csrc/shaders.cuh (V, HAS_FRAGMENT, BLEND_IGNORES_OLD, Uniforms, VERTEX_BYTES, vertex(),
+ * fragment(), blend()).  It is compiled with --fmad=false for sm_100a like the built-in pipelines.  On success
+ * *out_pipeline_id (>= EUC_PIPE_USER_BASE) can be used as euc_pipeline_desc.pipeline_id with this context
+ * (TriangleList only).  The compile log of the last call is available through euc_pipeline_log(). */
+#define EUC_PIPE_USER_BASE 1000
+int euc_pipeline_register(euc_ctx* ctx, const char* source, const char* struct_name, int32_t* out_pipeline_id);
+const char* euc_pipeline_log(euc_ctx* ctx);
+
 /* n_draws independent renders in one launch sequence. `uniforms` holds n_draws blocks of
  * desc->uniform_bytes each (desc->uniforms is ignored). Draw i renders into layer draws[i].layer. */
 int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_batch_draw* draws,
