@@ -184,7 +184,6 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     const int resident = ops.resident(msaa);  // CTAs of the raster kernel that fit one SM (sets its smem attribute once)
     if (resident <= 0) return fail(ctx, EUC_E_CUDA, "raster kernel occupancy query failed");
     // persistent grid: one resident set of CTAs; warps take tiles from a ticket counter (counters[4], zeroed per render)
-    prm.static_tiles = 0u;
     const uint32_t pblocks = std::min<uint32_t>(rblocks, (uint32_t)(ctx->sm_count * resident));
     const bool resolve = ops.defer && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
     if (resolve) {

@@ -87,7 +87,6 @@ struct Params {
     uint32_t list_capacity;
     int32_t prim_kind;      // euc_primitive_kind
     uint32_t cta_bin;       // 1: primitives covering > 256 tiles are binned by the whole CTA (few, huge primitives)
-    uint32_t static_tiles;  // 1: warp w of CTA b walks tile 4b+w only; 0: warps take tiles from a ticket counter
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
     int32_t stats;
@@ -1314,15 +1313,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, EUC_RASTER_MIN_CTAS) raster
     if (render_aborted(p)) return;
     uint32_t phase = 0, nfrag = 0;
     unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
-    for (uint32_t it = 0;; ++it) {
+    for (;;) {
         uint32_t tile = 0;
-        if (p.static_tiles) {  // one tile per warp, grid sized by the frame
-            if (it) break;
-            tile = blockIdx.x * RASTER_WARPS + warp;
-        } else {
-            if (lane == 0) tile = atomicAdd(ticket, 1u);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-        }
+        if (lane == 0) tile = atomicAdd(ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
         const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
         phase = res.x;
