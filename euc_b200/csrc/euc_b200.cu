@@ -184,7 +184,16 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     const int resident = ops.resident(msaa);  // CTAs of the raster kernel that fit one SM (sets its smem attribute once)
     if (resident <= 0) return fail(ctx, EUC_E_CUDA, "raster kernel occupancy query failed");
     // persistent grid: one resident set of CTAs; warps take tiles from a ticket counter (counters[4], zeroed per render)
-    const uint32_t pblocks = std::min<uint32_t>(rblocks, (uint32_t)(ctx->sm_count * resident));
+    // Balanced: every warp should walk the same number of tiles, otherwise the kernel lasts as long as the unlucky
+    // warps with one tile more (with 1.4 tiles per resident warp that is 2 tile-times instead of 1.4; fewer warps per
+    // SM run proportionally faster on this issue-bound kernel, so nothing is lost by launching fewer).
+    const uint32_t ty_lo = prm.row_begin / TILE, ty_hi = (std::min(prm.row_end, prm.h) + TILE - 1) / TILE;
+    const uint64_t n_active = (uint64_t)(ty_hi - ty_lo) * prm.tiles_x * prm.layers;
+    const uint64_t max_warps = (uint64_t)ctx->sm_count * resident * RASTER_WARPS;
+    const uint64_t tiles_per_warp = std::max<uint64_t>(1, (n_active + max_warps - 1) / max_warps);
+    const uint64_t want_warps = (n_active + tiles_per_warp - 1) / tiles_per_warp;
+    const uint32_t pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((want_warps + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
+    (void)rblocks;
     const bool resolve = ops.defer && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
     if (resolve) {
         const size_t wb = (size_t)prm.w * prm.h * prm.layers * 4;

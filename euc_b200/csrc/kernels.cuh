@@ -1313,10 +1313,16 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, EUC_RASTER_MIN_CTAS) raster
     if (render_aborted(p)) return;
     uint32_t phase = 0, nfrag = 0;
     unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
+    // tickets enumerate only the tile rows that intersect the rendered rows [row_begin, row_end)
+    const uint32_t ty_lo = p.row_begin / TILE, ty_hi = (min(p.row_end, p.h) + TILE - 1) / TILE;
+    const uint32_t per_layer = (ty_hi - ty_lo) * p.tiles_x, n_active = per_layer * p.layers;
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= n_active) break;
+        const uint32_t lay = tk / per_layer;
+        const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
         if (tile >= n_tiles) break;
         const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
         phase = res.x;
