@@ -66,6 +66,10 @@ SYMBOLS = {
     "euc_buf_clear_rows": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
     "euc_buf_upload": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_buf_download": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "euc_host_alloc": (C.c_int, [_ctx_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "euc_host_free": (C.c_int, [_ctx_p, C.c_void_p]),
+    "euc_buf_download_async": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "euc_ticket_wait": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_buf_device_ptr": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "euc_buf_size": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "euc_buf_wrap": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),

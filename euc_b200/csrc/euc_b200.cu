@@ -57,6 +57,8 @@ struct euc_ctx {
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
     int sm_count = 148;
     uint64_t launches = 0;
+    std::unordered_map<uint64_t, cudaEvent_t> tickets;  // pending asynchronous read-backs
+    uint64_t next_ticket = 1;
     bool profiling = false;
     cudaEvent_t ev_counts = nullptr, ev_setup = nullptr;
     cudaStream_t aux = nullptr;  // counter read-back
@@ -571,6 +573,7 @@ int euc_shutdown(euc_ctx* ctx) {
     for (auto& kv : ctx->geoms) if (kv.second.owned) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
     Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
     for (Scratch* s : ss) cudaFree(s->p);
+    for (auto& kv : ctx->tickets) cudaEventDestroy(kv.second);
     if (ctx->user) {
         for (auto& kv : ctx->user->pipes) { if (rt_api().ok) rt_api().ModuleUnload(kv.second->mod); delete kv.second; }
         delete ctx->user;
@@ -732,6 +735,46 @@ int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes) {
     if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "download of %zu bytes from a buffer of %zu bytes", bytes, it->second.bytes);
     if (bytes) CU(cudaMemcpyAsync(host, it->second.d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return EUC_OK;
+}
+
+int euc_host_alloc(euc_ctx* ctx, size_t bytes, void** out_ptr) {
+    if (!ctx || !out_ptr) return EUC_E_INVALID;
+    CU(cudaSetDevice(ctx->dev));
+    CU(cudaMallocHost(out_ptr, std::max<size_t>(bytes, 1)));
+    return EUC_OK;
+}
+
+int euc_host_free(euc_ctx* ctx, void* ptr) {
+    if (!ctx) return EUC_E_INVALID;
+    if (ptr) CU(cudaFreeHost(ptr));
+    return EUC_OK;
+}
+
+int euc_buf_download_async(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes, uint64_t* out_ticket) {
+    if (!ctx || !host || !out_ticket) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "download of %zu bytes from a buffer of %zu bytes", bytes, it->second.bytes);
+    if (bytes) CU(cudaMemcpyAsync(host, it->second.d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, ctx->stream));
+    const uint64_t t = ctx->next_ticket++;
+    ctx->tickets[t] = ev;
+    *out_ticket = t;
+    return EUC_OK;
+}
+
+int euc_ticket_wait(euc_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->tickets.find(ticket);
+    if (it == ctx->tickets.end()) return fail(ctx, EUC_E_INVALID, "unknown or already consumed ticket");
+    cudaEvent_t ev = it->second;
+    ctx->tickets.erase(it);
+    cudaError_t e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(ctx, EUC_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
     return EUC_OK;
 }
 

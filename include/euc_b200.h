@@ -203,6 +203,14 @@ int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel);                
 int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t row_begin, uint32_t row_end);
 int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes);       /* row-major, x + w*y, layer-major */
 int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes);           /* blocking */
+/* Row N4 (host I/O around the path): pinned host memory and asynchronous read-back, so that a consumer in the style of
+ * `win.update_with_buffer(color.raw(), ..)` (examples/teapot.rs:224) can keep several frames in flight.
+ * euc_buf_download_async returns at once; *out_ticket is complete when the bytes are in `host` (which should come from
+ * euc_host_alloc for a truly asynchronous copy).  euc_ticket_wait blocks on one ticket only, not on the whole stream. */
+int euc_host_alloc(euc_ctx* ctx, size_t bytes, void** out_ptr);
+int euc_host_free(euc_ctx* ctx, void* ptr);
+int euc_buf_download_async(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes, uint64_t* out_ticket);
+int euc_ticket_wait(euc_ctx* ctx, uint64_t ticket);
 int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes);
 int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* layers);
 /* Wrap caller-owned device memory (e.g. a slice of a collective's receive buffer) as a Buffer2d. Not freed by destroy. */
