@@ -239,18 +239,32 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
             hz[i] = clip.z;
             hw[i] = clip.w;
         }
-        // triangles.rs:64
-        float ex[3], ey[3], ez[3];
+        // Row-restricted renders (multi-GPU bands): every rank runs setup over all primitives, so the ones that miss its
+        // rows leave right after the vertex stage, on a y-only evaluation of the same bounds as below (:64, :110-139).
+        bool offband_early = false;
+        if (p.row_begin > 0u || p.row_end < p.h) {
+            const float size_yf = (float)p.h;
+            const float s0 = size_yf * ((hy[0] / hw[0]) * -0.5f + 0.5f), s1 = size_yf * ((hy[1] / hw[1]) * -0.5f + 0.5f),
+                        s2 = size_yf * ((hy[2] / hw[2]) * -0.5f + 0.5f);
+            const uint32_t eby0 = r_as_usize_clamped(r_min(r_min(s0, s1), s2) + 0.0f, 0u, p.h);
+            const uint32_t eby1 = r_as_usize_clamped(r_max(r_max(s0, s1), s2) + 1.0f, 0u, p.h);
+            offband_early = eby1 <= p.row_begin || eby0 >= p.row_end || eby1 <= eby0;
+        }
+        float ex[3] = {0.0f, 0.0f, 0.0f}, ey[3] = {0.0f, 0.0f, 0.0f}, ez[3] = {0.0f, 0.0f, 0.0f};
+        float winding = 0.0f;
+        bool culled = offband_early;
+        if (!offband_early) {
+            // triangles.rs:64
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { ex[i] = hx[i] / hw[i]; ey[i] = hy[i] / hw[i]; ez[i] = hz[i] / hw[i]; }
-        // triangles.rs:67-70: cross(e1-e0, e2-e0).z
-        float ax = ex[1] - ex[0], ay = ey[1] - ey[0];
-        float bx = ex[2] - ex[0], by = ey[2] - ey[0];
-        float winding = ax * by - ay * bx;
-        bool culled = false;
-        if (p.cull != EUC_CULL_NONE) {
-            float cull_dir = p.cull == EUC_CULL_BACK ? 1.0f : -1.0f;
-            culled = winding * cull_dir < 0.0f;  // :73-77
+            for (int i = 0; i < 3; ++i) { ex[i] = hx[i] / hw[i]; ey[i] = hy[i] / hw[i]; ez[i] = hz[i] / hw[i]; }
+            // triangles.rs:67-70: cross(e1-e0, e2-e0).z
+            const float ax = ex[1] - ex[0], ay = ey[1] - ey[0];
+            const float bx = ex[2] - ex[0], by = ey[2] - ey[0];
+            winding = ax * by - ay * bx;
+            if (p.cull != EUC_CULL_NONE) {
+                const float cull_dir = p.cull == EUC_CULL_BACK ? 1.0f : -1.0f;
+                culled = winding * cull_dir < 0.0f;  // :73-77
+            }
         }
         if (oob) culled = true;
         // :78-80 reverse vertex order when winding >= 0 (conditional swap of vertices 0 and 2)
