@@ -1010,6 +1010,8 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
                 const float d0 = q0.w, d1 = q1.x, d2 = q1.y, du = d2 - d0 - d1;
                 const float i0 = 1.0f / d0, i1 = 1.0f / d1, iu = 1.0f / du;
+                // an edge whose reciprocal overflowed (denormal slope) must not constrain: it selects like a zero slope below
+                const float e0 = fabsf(i0) < 3.0e38f ? d0 : 0.0f, e1 = fabsf(i1) < 3.0e38f ? d1 : 0.0f, eu = fabsf(iu) < 3.0e38f ? du : 0.0f;
                 const float kerr = (float)(x1 - x0 + 8u) * 1.1920929e-07f;  // (k + 8) * 2^-23
                 const float x1f = (float)x1;
                 const float mx0 = fabsf(d0) * x1f, mx1 = fabsf(d1) * x1f, mx2 = fabsf(d2) * x1f;
@@ -1026,9 +1028,9 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                     const float Au = A2 - A0 - A1;
                     const float t0 = (-m0 - A0) * i0, t1 = (-m1 - A1) * i1, tu = (-mu - Au) * iu;
                     // d > 0: x >= t;  d < 0: x <= t;  d == 0: the whole row is out when A < -m
-                    float lo = d0 > 0.0f ? t0 : -BIG, hi = d0 < 0.0f ? t0 : BIG;
-                    lo = fmaxf(lo, d1 > 0.0f ? t1 : -BIG); hi = fminf(hi, d1 < 0.0f ? t1 : BIG);
-                    lo = fmaxf(lo, du > 0.0f ? tu : -BIG); hi = fminf(hi, du < 0.0f ? tu : BIG);
+                    float lo = e0 > 0.0f ? t0 : -BIG, hi = e0 < 0.0f ? t0 : BIG;
+                    lo = fmaxf(lo, e1 > 0.0f ? t1 : -BIG); hi = fminf(hi, e1 < 0.0f ? t1 : BIG);
+                    lo = fmaxf(lo, eu > 0.0f ? tu : -BIG); hi = fminf(hi, eu < 0.0f ? tu : BIG);
                     const bool dead = (d0 == 0.0f && A0 < -m0) || (d1 == 0.0f && A1 < -m1) || (du == 0.0f && Au < -mu);
                     const float ilo = ceilf(lo - slack), ihi = floorf(hi + slack);  // integer pixel range that can pass
                     const bool ok0 = seg0 && !dead && fmaxf(xa0, ilo) <= fminf(xb0, ihi);

@@ -83,6 +83,36 @@ def test_random_triangles_blend(w, h, size, n):
     assert gs["primitives"] == rs["primitives"] == n
 
 
+def _axis_aligned_tris(n, seed, w, h):
+    """Right triangles with exactly horizontal and vertical edges on whole / half pixel positions: two of the three
+    barycentric weights have a zero, or a cancellation-sized (down to denormal), slope along x or y."""
+    r = scenes.u01(seed, n * 8).reshape(n, 8)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    px0 = np.floor(r[:, 0] * w) + (r[:, 6] < 0.5) * 0.5
+    py0 = np.floor(r[:, 1] * h) + (r[:, 7] < 0.5) * 0.5
+    ex = np.floor(1 + r[:, 2] * 40) * np.where(r[:, 3] < 0.5, -1, 1)
+    ey = np.floor(1 + r[:, 4] * 40) * np.where(r[:, 5] < 0.5, -1, 1)
+    sx = np.stack([px0, px0 + ex, px0], axis=1)
+    sy = np.stack([py0, py0, py0 + ey], axis=1)
+    wv = np.where(r[:, 5:6] < 0.25, 1.0, 0.5 + r[:, 2:5])  # a quarter of them without perspective
+    v["pos"][:, :, 0] = (sx / w * 2 - 1) * wv
+    v["pos"][:, :, 1] = (sy / h * 2 - 1) * wv
+    v["pos"][:, :, 2] = (0.1 + 0.8 * r[:, 3:4]) * wv
+    v["pos"][:, :, 3] = wv
+    v["rgba"][:, :, :3] = r[:, None, 5:8]
+    v["rgba"][:, :, 3] = 0.5
+    return v.astype(e.VERTEX_P4C4).reshape(-1)
+
+
+@pytest.mark.parametrize("w,h,seed", [(640, 480, 1), (1024, 96, 2), (4096, 48, 3)])
+def test_axis_aligned_edges(w, h, seed):
+    verts = _axis_aligned_tris(4000, 0xA715 + seed, w, h)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), verts, w, h, clear_px=0xFF000000)
+    assert_depth_bit_exact(gz, rz, f"axis aligned {w}x{h}")
+    assert_colour_within_1lsb(gpx, rpx, f"axis aligned {w}x{h}")
+    assert gs["fragments"] == rs["fragments"]
+
+
 @pytest.mark.parametrize("cull", [e.CullMode.NONE, e.CullMode.Back, e.CullMode.Front])
 @pytest.mark.parametrize("coords", ["VULKAN", "OPENGL", "noclip"])
 def test_nasty_triangles_modes(cull, coords):
