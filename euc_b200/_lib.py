@@ -6,7 +6,8 @@ import os
 from . import abi
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libeuc_b200.so")
+# EUC_B200_LIB selects another build of the same library (kernel A/B experiments, tools/ab.sh); never a fallback
+LIB_PATH = os.environ.get("EUC_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libeuc_b200.so")
 
 
 class EucError(RuntimeError):

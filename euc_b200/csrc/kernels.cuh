@@ -684,8 +684,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // With any depth mode that is the reference's final pixel: blend(_, fragment(last passing)) (pipeline.rs:574-576).
 // -------------------------------------------------------------------------------------------------------
 constexpr int RASTER_WARPS = 4;
+// Resident CTAs per SM the raster kernel is compiled for (register cap 65536 / (128 * n)).  Measured on C4 / C5: 6 CTAs
+// (80 registers, no spills) beat the unconstrained 107-register build by 12 % / 14 %: the kernel is issue bound and needs
+// the warps.  The immediate-mode MSAA instantiations keep four corner fragments live and would spill at 80.
 #ifndef EUC_RASTER_MIN_CTAS
-#define EUC_RASTER_MIN_CTAS 1
+#define EUC_RASTER_MIN_CTAS 6
+#endif
+#ifndef EUC_ROUND64_MAX_REC_BYTES
+#define EUC_ROUND64_MAX_REC_BYTES 128u
 #endif
 constexpr int BATCH = 32;  // setup records per bulk-copy stage (== warp size: one lane-mask per lane)
 constexpr uint32_t NO_WINNER = 0xffffffffu;
@@ -710,7 +716,7 @@ constexpr int IDS_REGS = 128;      // lists up to this length are sorted, and th
 // and 32 when they are large: the stage size decides how many CTAs fit an SM (ncu on C5: 3 CTAs/SM, issue-active 49 %).
 template <class P, bool DEFER> struct StageGeom {
     static constexpr uint32_t REC_WORDS = DEFER ? (uint32_t)REC_BASE_WORDS : (uint32_t)RecLayout<P>::WORDS;  // words of a record kept in the stage
-    static constexpr uint32_t BATCHES = REC_WORDS * 4u <= 128u ? 2u : 1u;                                    // batches of 32 records per round
+    static constexpr uint32_t BATCHES = REC_WORDS * 4u <= EUC_ROUND64_MAX_REC_BYTES ? 2u : 1u;                                    // batches of 32 records per round
     static constexpr uint32_t WORDS = BATCHES * BATCH * REC_WORDS;                                           // stage words per warp
 };
 
@@ -816,6 +822,71 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
         const float t1 = right.t0[c] * omy + right.t1[c] * fracty;  // weighted_sum2(t10, t11, 1-fy, fy)
         frag[c] = t0 * omx + t1 * fractx;                           // weighted_sum2(t0, t1, 1-fx, fx)
     }
+}
+
+// One pixel of the coverage + depth loop on the fast path (LESS / GREATER with depth write, no per-fragment z clip),
+// triangles.rs:262-271, :301 and pipeline.rs:519-538.  Written in PTX so that the whole test stays ONE predicate chain
+// (range, three weights through a NaN-propagating 3-input min, depth) and the chain advance is three predicated adds:
+// the C++ form compiled to a select per condition and per weight, and the kernel is bound by the ALU pipe (ncu).
+// Every f32 operation carries .rn and is therefore never contracted; operation order is the reference's.
+//   d     sgn*depth of pixel J (register)        mask  bit J set when the fragment passed
+//   w0..2 chain values at pixel J, advanced to J+1 when J >= jlo       [jlo, jhi) pixels of the segment inside row_range
+template <int J, bool DEFER>
+__device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, float& w1, float& w2, uint32_t& mask, const float dx0,
+                                        const float dx1, const float dx2, const float z0, const float z1, const float z2, const float dsgn,
+                                        const uint32_t jlo, const uint32_t jhi, const uint32_t tri) {
+// the 3-input min (FMNMX3) needs PTX ISA 8.8 (CUDA 12.9); older NVRTC builds (e.g. the one bundled with torch, which
+// wins the dlopen when torch is loaded first) get two 2-input ones
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ > 12 || (__CUDACC_VER_MAJOR__ == 12 && __CUDACC_VER_MINOR__ >= 9))
+#define EUC_PX_MIN3 "min.NaN.f32 m, %1, %2, wu;\n"
+#else
+#define EUC_PX_MIN3 "min.NaN.f32 m, %1, %2;\n min.NaN.f32 m, m, wu;\n"
+#endif
+#define EUC_PX_BODY                                                                                                     \
+    "{\n"                                                                                                               \
+    ".reg .pred pa, pp;\n"                                                                                              \
+    ".reg .f32 wu, z, t, m;\n"                                                                                          \
+    "setp.le.u32 pa, %13, %15;\n"          /* jlo <= J: the chain advances from here on (:301) */                        \
+    "setp.gt.and.u32 pp, %14, %15, pa;\n"  /* J < jhi: inside row_range (:262) */                                        \
+    "sub.rn.f32 wu, %3, %1;\n"                                                                                          \
+    "sub.rn.f32 wu, wu, %2;\n"             /* :264 w_unbalanced[2] = w2 - w0 - w1 */                                     \
+    "mul.rn.f32 z, %9, %1;\n"                                                                                           \
+    "mul.rn.f32 t, %10, %2;\n"                                                                                          \
+    "add.rn.f32 z, z, t;\n"                                                                                             \
+    "mul.rn.f32 t, %11, wu;\n"                                                                                          \
+    "add.rn.f32 z, z, t;\n"                /* :269 z = z0*w0 + z1*w1 + z2*wu */                                          \
+    "mul.rn.f32 z, z, %12;\n"              /* sgn-space (exact) */                                                       \
+    EUC_PX_MIN3                            /* all three >= 0 (:267); NaN in any weight fails like the three compares */  \
+    "setp.ge.and.f32 pp, m, 0f00000000, pp;\n"                                                                          \
+    "setp.lt.and.f32 pp, z, %0, pp;\n"     /* pipeline.rs:519-526 */                                                     \
+    "@pp mov.f32 %0, z;\n"                 /* pipeline.rs:536-538 */                                                     \
+    "@pp or.b32 %4, %4, %16;\n"
+#define EUC_PX_TAIL                                                                                                     \
+    "@pa add.rn.f32 %1, %1, %6;\n"                                                                                      \
+    "@pa add.rn.f32 %2, %2, %7;\n"                                                                                      \
+    "@pa add.rn.f32 %3, %3, %8;\n"                                                                                      \
+    "}\n"
+#define EUC_PX_OPERANDS                                                                                                 \
+    : "+f"(d), "+f"(w0), "+f"(w1), "+f"(w2), "+r"(mask), "+r"(cwj)                                                      \
+    : "f"(dx0), "f"(dx1), "f"(dx2), "f"(z0), "f"(z1), "f"(z2), "f"(dsgn), "r"(jlo), "r"(jhi), "n"(J), "n"(1 << J), "r"(tri)
+    if constexpr (DEFER) {
+        asm(EUC_PX_BODY "@pp mov.b32 %5, %17;\n" EUC_PX_TAIL EUC_PX_OPERANDS);
+    } else {
+        asm(EUC_PX_BODY EUC_PX_TAIL EUC_PX_OPERANDS);
+    }
+#undef EUC_PX_OPERANDS
+#undef EUC_PX_BODY
+#undef EUC_PX_MIN3
+#undef EUC_PX_TAIL
+}
+
+// sm_100 FADD2: two IEEE f32 additions per issue slot, each half rounded exactly like the scalar instruction.  (Packed
+// multiplies are NOT used anywhere: ptxas contracts a mul.f32x2 that feeds an add.f32x2 into FFMA2 even with .rn and
+// -fmad=false.  In the pixel loop a predicated FADD2 compiles to FADD2 + two selects, which costs more than it saves.)
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
 
 // One 16x16 tile, walked by one warp.
@@ -979,6 +1050,17 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         mbar_wait(&bar[0], phase);
         phase ^= 1u;
         const uint32_t* stage = recs_sm;
+        // the PTX pixel loop (px_step) covers the common case; a round in which any record needs the per-fragment z clip
+        // (:271: some vertex failed the clip test), and every other depth mode, takes the general loops
+        bool fast_px = false;
+        if (!LINES && fast_depth && p.depth_write) {
+            bool need_zc = false;
+            if (p.zclip) {
+                if (lane < cnt0) need_zc = (stage[lane * SW + R_FLAGS] & 1u) == 0u;
+                if (NB > 1 && lane < cnt1) need_zc = need_zc || (stage[(BATCH + lane) * SW + R_FLAGS] & 1u) == 0u;
+            }
+            fast_px = !__any_sync(0xffffffffu, need_zc);
+        }
 
         // lane t: which lanes (row, half) can triangle t cover?  Bounding box first, then per tile row the range of
         // integer x on which all three weights can be non-negative.  Each weight is linear in x (w = A + d*x); euc
@@ -1008,48 +1090,71 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
             if (y1 > tile_y0 && y0 < tile_y0 + TILE && rb > ra && x1 > x0) {
                 const bool seg0 = x0 < tile_x0 + 8u && x1 > tile_x0, seg1 = x0 < tile_x0 + 16u && x1 > tile_x0 + 8u;
                 const float4 q0 = rec4[0], q1 = rec4[1], q2 = rec4[2];  // o0 o1 o2 dx0 | dx1 dx2 dy0 dy1 | dy2 z0 z1 z2
-                const float d0 = q0.w, d1 = q1.x, d2 = q1.y, du = d2 - d0 - d1;
-                const float i0 = 1.0f / d0, i1 = 1.0f / d1, iu = 1.0f / du;
-                // an edge whose reciprocal overflowed (denormal slope) must not constrain: it selects like a zero slope below
-                const float e0 = fabsf(i0) < 3.0e38f ? d0 : 0.0f, e1 = fabsf(i1) < 3.0e38f ? d1 : 0.0f, eu = fabsf(iu) < 3.0e38f ? du : 0.0f;
-                const float kerr = (float)(x1 - x0 + 8u) * 1.1920929e-07f;  // (k + 8) * 2^-23
-                const float x1f = (float)x1;
-                const float mx0 = fabsf(d0) * x1f, mx1 = fabsf(d1) * x1f, mx2 = fabsf(d2) * x1f;
+                // weight e at pixel (x, y): a + b*y + d*x in exact arithmetic (e = 0, 1 and the unbalanced third, :264)
+                const float a0 = q0.x, a1 = q0.y, a2 = q0.z, d0 = q0.w, d1 = q1.x, d2 = q1.y, b0 = q1.z, b1 = q1.w, b2 = q2.x;
+                const float au = a2 - a0 - a1, bu = b2 - b0 - b1, du = d2 - d0 - d1;
+                const float x1f = (float)x1, ymaxf = (float)(tile_y0 + (uint32_t)TILE);
+                // Error budget in weight units, one value per edge for the whole tile: the chain of k <= x1 - x0 additions,
+                // its start, the rounding of a + b*y and of the fused evaluation below are each bounded by a few 2^-24 of
+                // S = |a| + |b|*ymax + |d|*x1 (k + 2 for the chain, 2 for a + b*y, 3 for the fused evaluation and its two
+                // coefficients); (k + 12) * 2^-23 * S is at least twice their sum.
+                const float kerr = (float)(x1 - x0 + 12u) * 1.1920929e-07f;
+                const float s0 = (fabsf(a0) + fabsf(b0) * ymaxf) + fabsf(d0) * x1f, s1 = (fabsf(a1) + fabsf(b1) * ymaxf) + fabsf(d1) * x1f,
+                            s2 = (fabsf(a2) + fabsf(b2) * ymaxf) + fabsf(d2) * x1f;
+                const float m0 = kerr * s0, m1 = kerr * s1, mu = 2.0f * (kerr * ((s0 + s1) + s2));
+                const float slack = 0.01f + x1f * 1e-5f;  // pixels: rounding of the reciprocal and of the products (2^-22 of |x| <= x1)
+                const float BIG = 3.0e38f;
+                // Per edge the admissible x of row y is x >= t(y) (d > 0) or x <= t(y) (d < 0), t(y) = (-m - a - b*y) / d, which is
+                // linear in y: t = y*P + Q, one FMA per row.  An edge that is not a bound of that kind contributes -/+BIG.  A
+                // slope too small to invert (zero, denormal: the weight is constant along the row) is replaced by +-1e-30, which
+                // turns t into -/+huge according to the sign of a + b*y + m, i.e. the whole row passes or fails that edge.
+                float PL0, QL0, PH0, QH0, PL1, QL1, PH1, QH1, PLu, QLu, PHu, QHu;
+                auto edge = [&](float a, float b, float d, float m, float& PL, float& QL, float& PH, float& QH) {
+                    float i = 1.0f / d;
+                    if (!(fabsf(i) < 1.0e30f)) i = copysignf(1.0e30f, d);
+                    const float tp = -b * i, tq = (-m - a) * i;
+                    const bool lower = i > 0.0f;
+                    PL = lower ? tp : 0.0f; QL = lower ? tq - slack : -BIG;
+                    PH = lower ? 0.0f : tp; QH = lower ? BIG : tq + slack;
+                };
+                edge(a0, b0, d0, m0, PL0, QL0, PH0, QH0);
+                edge(a1, b1, d1, m1, PL1, QL1, PH1, QH1);
+                edge(au, bu, du, mu, PLu, QLu, PHu, QHu);
                 // segment end points clamped to the bounds: [xa, xb] inclusive pixel coordinates
                 const float xa0 = (float)max(tile_x0, x0), xb0 = (float)min(tile_x0 + 7u, x1 - 1u);
                 const float xa1 = (float)max(tile_x0 + 8u, x0), xb1 = (float)min(tile_x0 + 15u, x1 - 1u);
-                const float slack = 0.01f + x1f * 1e-5f;
-                const float BIG = 3.0e38f;
-                for (uint32_t r = ra; r < rb; ++r) {
-                    const float yr = (float)(tile_y0 + r);
-                    const float A0 = q0.x + q1.z * yr, A1 = q0.y + q1.w * yr, A2 = q0.z + q2.x * yr;
-                    const float m0 = kerr * (fabsf(A0) + mx0), m1 = kerr * (fabsf(A1) + mx1), m2 = kerr * (fabsf(A2) + mx2);
-                    const float mu = 2.0f * (m0 + m1 + m2);
-                    const float Au = A2 - A0 - A1;
-                    const float t0 = (-m0 - A0) * i0, t1 = (-m1 - A1) * i1, tu = (-mu - Au) * iu;
-                    // d > 0: x >= t;  d < 0: x <= t;  d == 0: the whole row is out when A < -m
-                    float lo = e0 > 0.0f ? t0 : -BIG, hi = e0 < 0.0f ? t0 : BIG;
-                    lo = fmaxf(lo, e1 > 0.0f ? t1 : -BIG); hi = fminf(hi, e1 < 0.0f ? t1 : BIG);
-                    lo = fmaxf(lo, eu > 0.0f ? tu : -BIG); hi = fminf(hi, eu < 0.0f ? tu : BIG);
-                    const bool dead = (d0 == 0.0f && A0 < -m0) || (d1 == 0.0f && A1 < -m1) || (du == 0.0f && Au < -mu);
-                    const float ilo = ceilf(lo - slack), ihi = floorf(hi + slack);  // integer pixel range that can pass
-                    const bool ok0 = seg0 && !dead && fmaxf(xa0, ilo) <= fminf(xb0, ihi);
-                    const bool ok1 = seg1 && !dead && fmaxf(xa1, ilo) <= fminf(xb1, ihi);
-                    m |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2u * r);
+                if (!(fminf(fminf(s0, s1), s2) > 1.0e-18f)) {
+                    // degenerate weights (or NaN): the budget above is meaningless, every segment inside the bounds is visited
+                    m = (((seg0 ? 0x55555555u : 0u) | (seg1 ? 0xaaaaaaaau : 0u)) >> (2u * ra)) << (2u * ra);
+                    if (rb < 16u) m &= (1u << (2u * rb)) - 1u;
+                } else {
+                    float yr = (float)(tile_y0 + ra);
+                    for (uint32_t r = ra; r < rb; ++r) {
+                        // NaN (from Inf - Inf or NaN vertices) is ignored by fmaxf / fminf and by the comparisons: never rejects
+                        const float lo = fmaxf(fmaxf(__fmaf_rn(yr, PL0, QL0), __fmaf_rn(yr, PL1, QL1)), __fmaf_rn(yr, PLu, QLu));
+                        const float hi = fminf(fminf(__fmaf_rn(yr, PH0, QH0), __fmaf_rn(yr, PH1, QH1)), __fmaf_rn(yr, PHu, QHu));
+                        const float ilo = ceilf(lo), ihi = floorf(hi);  // integer pixel range that can pass
+                        const bool ok0 = seg0 && !(fmaxf(xa0, ilo) > fminf(xb0, ihi));
+                        const bool ok1 = seg1 && !(fmaxf(xa1, ilo) > fminf(xb1, ihi));
+                        m |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2u * r);
+                        yr += 1.0f;
+                    }
                 }
             }
         }
         return m;
         };
         // transpose: own bit t <=> primitive t of the round touches this lane
-        auto transpose = [&](uint32_t m) -> uint32_t {
-            uint32_t own = 0;
+        // 32x32 bit-matrix transpose across the warp (row = lane) in five butterfly stages: lanes l and l^j exchange the
+        // off-diagonal j x j blocks (32 ballots cost ~6 instructions each)
+        auto transpose = [&](uint32_t x) -> uint32_t {
 #pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const uint32_t bits = __ballot_sync(0xffffffffu, (m >> l) & 1u);
-                if ((int)lane == l) own = bits;
+            for (uint32_t j = 16; j >= 1; j >>= 1) {
+                const uint32_t k = 0xffffffffu / ((1u << j) + 1u);  // bits whose index has bit j clear
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+                x = (lane & j) ? (((y >> j) & k) | (x & ~k)) : ((x & k) | ((y & k) << j));
             }
-            return row_ok ? own : 0u;
+            return row_ok ? x : 0u;
         };
         uint32_t own0 = transpose(lane_mask(lane, lane < cnt0));
         uint32_t own1 = (NB > 1 && cnt1) ? transpose(lane_mask(BATCH + lane, lane < cnt1)) : 0u;
@@ -1162,15 +1267,47 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 float w2 = (q0.z + q2.x * yf) + dx2 * r0f;
                 if (segx0 > r0) {
                     const uint32_t npre = segx0 - r0;
+#ifdef EUC_PX_F32X2
+                    unsigned long long w01 = pack_f32x2(w0, w1);
+                    const unsigned long long dx01 = pack_f32x2(dx0, dx1);
+#pragma unroll 4
+                    for (uint32_t i = 0; i < npre; ++i) {
+                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(w01) : "l"(dx01));
+                        w2 = w2 + dx2;
+                    }
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(w0), "=f"(w1) : "l"(w01));
+#else
 #pragma unroll 4
                     for (uint32_t i = 0; i < npre; ++i) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }
+#endif
                 }
                 const float z0 = q2.y, z1 = q2.z, z2 = q2.w;
                 const float4 q5 = rec4[5];  // flags draw tri -
                 const bool zc = p.zclip && (__float_as_uint(q5.x) & 1u) == 0u;  // per-fragment z clip needed (:271)
                 const uint32_t tri_id = __float_as_uint(q5.z);
                 uint32_t passmask = 0;
-                if (fast_depth) {
+#ifdef EUC_DBG_COUNT  // development builds only: the fragment counter reports visits (1), covered pixels (2), visits without coverage (3)
+                {
+                    float a0 = w0, a1 = w1, a2 = w2;
+                    uint32_t cov = 0;
+                    for (uint32_t j = 0; j < 8u; ++j) {
+                        const float au = a2 - a0 - a1;
+                        if (((inmask >> j) & 1u) && a0 >= 0.0f && a1 >= 0.0f && au >= 0.0f) ++cov;
+                        if (j >= jlo) { a0 = a0 + dx0; a1 = a1 + dx1; a2 = a2 + dx2; }
+                    }
+                    nfrag += EUC_DBG_COUNT == 1 ? 1u : (EUC_DBG_COUNT == 2 ? cov : (cov == 0u ? 1u : 0u));
+                }
+#endif
+                if (fast_px) {  // warp-uniform: LESS / GREATER with depth write, no record of this round needs the z clip
+                    px_step<0, DEFER>(depth[0], cw[0], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<1, DEFER>(depth[1], cw[1], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<2, DEFER>(depth[2], cw[2], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<3, DEFER>(depth[3], cw[3], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<4, DEFER>(depth[4], cw[4], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<5, DEFER>(depth[5], cw[5], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<6, DEFER>(depth[6], cw[6], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    px_step<7, DEFER>(depth[7], cw[7], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                } else if (fast_depth) {
                     // z clip as bounds: when every vertex passed the clip the per-fragment test is skipped (:271), i.e.
                     // the bounds are infinite.  A NaN z fails here but would fail the depth comparison anyway.
                     const float zlo = zc ? p.zmin : -__int_as_float(0x7f800000), zhi = zc ? p.zmax : __int_as_float(0x7f800000);
@@ -1207,7 +1344,9 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                     }
                     if ((uint32_t)j >= jlo) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }     // :301
                 }
+#ifndef EUC_DBG_COUNT
                 nfrag += __popc(passmask);
+#endif
                 if (QUEUE && passmask && shade_px) {
                     queue[qn++] = (uint16_t)((t << 8) | passmask);
                     qf += __popc(passmask);
@@ -1312,7 +1451,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
 // Persistent kernel: every warp takes tiles from a ticket counter until none are left, so the grid is sized by the
 // machine (SMs x resident CTAs), not by the frame, and there is no partial last wave.
 template <class P, bool MSAA, bool DEFER, bool LINES>
-__global__ void __launch_bounds__(RASTER_WARPS * 32, EUC_RASTER_MIN_CTAS) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
+__global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_RASTER_MIN_CTAS) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
     using L = RecLayout<P>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;

@@ -31,6 +31,10 @@ __device__ __forceinline__ uint32_t r_as_u8(float f) {
     uint32_t v = __float2uint_rz(f);  // NaN -> 0, negative -> 0
     return v > 255u ? 255u : v;
 }
+// `f.max(0.0).min(255.0) as u8`: the saturating cast alone has the same value for every input (NaN: max(NaN, 0) = 0 and
+// the cast of NaN is 0; f < 0: both 0; f > 255: both 255; in between the clamp is the identity), so the two
+// NaN-aware min/max are not materialised.
+__device__ __forceinline__ uint32_t r_clamp255_as_u8(float f) { return r_as_u8(f); }
 // vek Mat4<f32> * Vec4<f32> (column-major): cols[0]*x, then fused mul_add per remaining column (see DESIGN.md
 // "Unpinned beliefs": vek 0.17 is not in the reference tree).  __fmaf_rn is never split or re-fused by --fmad.
 __device__ __forceinline__ float4 mat4_mul_vec4(const float* __restrict__ m, float x, float y, float z, float w) {

@@ -203,8 +203,8 @@ struct PipeBlendTris {
         float c0 = (n[0] * 255.0f) * a + (float)(old & 0xffu) * ia;
         float c1 = (n[1] * 255.0f) * a + (float)((old >> 8) & 0xffu) * ia;
         float c2 = (n[2] * 255.0f) * a + (float)((old >> 16) & 0xffu) * ia;
-        return pack_le(r_as_u8(r_min(r_max(c0, 0.0f), 255.0f)), r_as_u8(r_min(r_max(c1, 0.0f), 255.0f)),
-                       r_as_u8(r_min(r_max(c2, 0.0f), 255.0f)), 255u);
+        return pack_le(r_clamp255_as_u8(c0), r_clamp255_as_u8(c1),
+                       r_clamp255_as_u8(c2), 255u);
     }
 };
 
@@ -236,8 +236,8 @@ struct PipeVoxelIcon {
         float g = (n[1] * 255.0f) * a + og * ia;
         float b = (n[2] * 255.0f) * a + ob * ia;
         float A = a * 255.0f + oa * ia;
-        return pack_le(r_as_u8(r_min(r_max(b, 0.0f), 255.0f)), r_as_u8(r_min(r_max(g, 0.0f), 255.0f)),
-                       r_as_u8(r_min(r_max(r, 0.0f), 255.0f)), r_as_u8(r_min(r_max(A, 0.0f), 255.0f)));
+        return pack_le(r_clamp255_as_u8(b), r_clamp255_as_u8(g),
+                       r_clamp255_as_u8(r), r_clamp255_as_u8(A));
     }
 };
 

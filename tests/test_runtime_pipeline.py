@@ -101,9 +101,27 @@ def test_user_pipeline_compile_error_is_reported():
     assert ei.value.code == e.abi.E_INVALID and "user_pipeline.cu" in str(ei.value)
 
 
-def test_headers_are_nvrtc_clean():
+def _bundled_nvrtc():
+    """The NVRTC that ships with torch's CUDA wheels (older than the toolkit's): it is the one dlopen("libnvrtc.so.12")
+    finds when torch was imported first, so the headers must build with it too."""
+    try:
+        import nvidia.cuda_nvrtc as m
+    except ImportError:
+        return None
+    path = os.path.join(list(m.__path__)[0], "lib", "libnvrtc.so.12")
+    return path if os.path.exists(path) else None
+
+
+@pytest.mark.parametrize("which", ["toolkit", "bundled"])
+def test_headers_are_nvrtc_clean(which):
     """NVRTC needs no GPU to compile: the kernel headers plus the example user pipeline must build for sm_100a."""
     import subprocess, sys
+    env = dict(os.environ)
+    if which == "bundled":
+        lib = _bundled_nvrtc()
+        if lib is None:
+            pytest.skip("no bundled NVRTC in this environment")
+        env["NVRTC_LIB"] = lib
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nvrtc_check.py"), os.path.join(ROOT, "examples", "user_pipeline_tint.cu"), "TintPipe"],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.stdout.startswith("rc 0"), out.stdout + out.stderr

@@ -6,7 +6,7 @@ src, name = open(sys.argv[1]).read(), sys.argv[2]
 tu = '#include "kernels.cuh"\nnamespace eucb {\n#line 1 "user_pipeline.cu"\n' + src + "\n}\nusing EucUserPipe = eucb::" + name + ";\n" + \
      "constexpr bool EUC_USER_DEFER = EucUserPipe::HAS_FRAGMENT && EucUserPipe::BLEND_IGNORES_OLD;\n" + \
      'extern "C" __global__ void euc_user_info(unsigned int* out) { out[0] = EucUserPipe::V; out[5] = eucb::RecLayout<EucUserPipe>::BYTES; out[6] = (unsigned int)eucb::raster_smem_bytes<EucUserPipe, EUC_USER_DEFER>(); }\n'
-n = C.CDLL("/usr/local/cuda/lib64/libnvrtc.so.12")
+n = C.CDLL(os.environ.get("NVRTC_LIB", "/usr/local/cuda/lib64/libnvrtc.so.12"))
 prog = C.c_void_p()
 assert n.nvrtcCreateProgram(C.byref(prog), tu.encode(), b"euc_user_pipeline.cu", 0, None, None) == 0
 names = [b"eucb::setup_kernel<EucUserPipe>", b"eucb::raster_kernel<EucUserPipe, false, EUC_USER_DEFER, false>", b"eucb::raster_kernel<EucUserPipe, true, EUC_USER_DEFER, false>",
