@@ -217,6 +217,10 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
     uint2 bbox = make_uint2(0u, 0u);
     uint32_t layer = 0;
     bool oob = false;
+    TileRect r;
+    bool valid = false;
+    uint32_t nt = 0;
+    uint32_t sl[8];  // bin slots of a small primitive (fast path), taken early and consumed after the record store
 
     if (live) {
         const uint32_t d = find_draw(p, tri);
@@ -277,8 +281,43 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
             t = ez[0]; ez[0] = ez[2]; ez[2] = t;
         }
 
-        uint32_t* rec = rec_stage[threadIdx.x];
+        // :110-111 verts_screen and :114-139 bounds (clamped to the whole target here; the band clamp is applied per row in
+        // the raster kernel).  They only need the divided coordinates, so they come first: the bin appends below are then
+        // in flight during the rest of the set-up arithmetic and the record store.
+        float scx[3] = {0.0f, 0.0f, 0.0f}, scy[3] = {0.0f, 0.0f, 0.0f};
+        const float size_x = (float)p.w, size_y = (float)p.h;
         if (!culled) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                scx[i] = size_x * (ex[i] * 0.5f + 0.5f);
+                scy[i] = size_y * (ey[i] * -0.5f + 0.5f);
+            }
+            const uint32_t bx0 = r_as_usize_clamped(r_min(r_min(scx[0], scx[1]), scx[2]) + 0.0f, 0u, p.w);
+            const uint32_t by0 = r_as_usize_clamped(r_min(r_min(scy[0], scy[1]), scy[2]) + 0.0f, 0u, p.h);
+            const uint32_t bx1 = r_as_usize_clamped(r_max(r_max(scx[0], scx[1]), scx[2]) + 1.0f, 0u, p.w);
+            const uint32_t by1 = r_as_usize_clamped(r_max(r_max(scy[0], scy[1]), scy[2]) + 1.0f, 0u, p.h);
+            bbox = make_uint2(bx0 | (bx1 << 16), by0 | (by1 << 16));
+            // row-restricted renders (multi-GPU bands): primitives that miss this rank's rows are dropped here
+            if (by1 <= p.row_begin || by0 >= p.row_end || bx1 <= bx0 || by1 <= by0) bbox = make_uint2(0u, 0u);
+        }
+        p.tri_bbox[tri] = bbox;
+        valid = tile_rect(p, bbox, layer, r);
+        nt = valid ? r.ntx * r.nty : 0u;
+        if (p.bin_cap && valid && nt <= 8u) {
+            // fast path, small primitives: every tile owns bin_cap slots; all appends are issued back to back so that their
+            // round trips overlap, and the slots are consumed after the record has been written
+            uint32_t jj = 0, ii = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((uint32_t)k < nt) {
+                    sl[k] = atomicAdd(p.tile_count + (r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii), 1u);
+                    if (++ii == r.ntx) { ii = 0; ++jj; }
+                }
+            }
+        }
+
+        uint32_t* rec = rec_stage[threadIdx.x];
+        if (bbox.x | bbox.y) {  // neither culled nor off-band
             // :86-102 coords_to_weights
             const float a0 = hx[0], a1 = hy[0], a3 = hw[0];
             const float b0 = hx[1], b1 = hy[1], b3 = hw[1];
@@ -294,7 +333,6 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
             m[0][0] = (cb1 * c2 - cb2 * c1) * rec_det; m[0][1] = (cb2 * c0 - cb0 * c2) * rec_det; m[0][2] = (cb0 * c1 - cb1 * c0) * rec_det;
             m[1][0] = (c1 * ca2 - c2 * ca1) * rec_det; m[1][1] = (c2 * ca0 - c0 * ca2) * rec_det; m[1][2] = (c0 * ca1 - c1 * ca0) * rec_det;
             m[2][0] = n0 * rec_det; m[2][1] = n1 * rec_det; m[2][2] = n2 * rec_det;
-            const float size_x = (float)p.w, size_y = (float)p.h;
             const float sx = 2.0f / size_x, sy = -2.0f / size_y;  // to_ndc :44-48
             float cw[3][3];  // matmul(m, to_ndc) :345-355, all nine products kept
 #pragma unroll
@@ -303,18 +341,6 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
                 cw[i][1] = m[i][0] * 0.0f + m[i][1] * sy + m[i][2] * 0.0f;
                 cw[i][2] = m[i][0] * -1.0f + m[i][1] * 1.0f + m[i][2] * 1.0f;
             }
-            // :110-111 verts_screen
-            float scx[3], scy[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                scx[i] = size_x * (ex[i] * 0.5f + 0.5f);
-                scy[i] = size_y * (ey[i] * -0.5f + 0.5f);
-            }
-            // :114-139 bounds, clamped to the whole target here; the band clamp is applied per row in the raster kernel
-            const uint32_t bx0 = r_as_usize_clamped(r_min(r_min(scx[0], scx[1]), scx[2]) + 0.0f, 0u, p.w);
-            const uint32_t by0 = r_as_usize_clamped(r_min(r_min(scy[0], scy[1]), scy[2]) + 0.0f, 0u, p.h);
-            const uint32_t bx1 = r_as_usize_clamped(r_max(r_max(scx[0], scx[1]), scx[2]) + 1.0f, 0u, p.w);
-            const uint32_t by1 = r_as_usize_clamped(r_max(r_max(scy[0], scy[1]), scy[2]) + 1.0f, 0u, p.h);
             // :142-145 finite-difference weight deltas
             float o[3], wdx[3], wdy[3];
 #pragma unroll
@@ -337,11 +363,6 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
 #pragma unroll
                 for (int i = 0; i < 3; ++i) nvc = nvc && (p.zmin <= ez[i] && ez[i] <= p.zmax);
             }
-            bbox = make_uint2(bx0 | (bx1 << 16), by0 | (by1 << 16));
-            // row-restricted renders (multi-GPU bands): primitives that miss this rank's rows are dropped here
-            const bool offband = by1 <= p.row_begin || by0 >= p.row_end || bx1 <= bx0 || by1 <= by0;
-            if (offband) bbox = make_uint2(0u, 0u);
-            if (!offband) {
             float4* r4 = reinterpret_cast<float4*>(rec);
             r4[0] = make_float4(o[0], o[1], o[2], wdx[0]);
             r4[1] = make_float4(wdx[1], wdx[2], wdy[0], wdy[1]);
@@ -362,9 +383,7 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
 #pragma unroll
                 for (int k = 0; k < L::VPAD / 4; ++k) r4[6 + k] = make_float4(flat[4 * k], flat[4 * k + 1], flat[4 * k + 2], flat[4 * k + 3]);
             }
-            }
         }
-        p.tri_bbox[tri] = bbox;
     }
     if (__any_sync(0xffffffffu, oob) && oob) atomicOr(p.counters + 3, 1ull);
     {   // one bulk store per warp: records of primitives [warp_first, warp_first + nrec)
@@ -378,31 +397,20 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         }
     }
 
-    // per-tile population count
-    TileRect r;
-    bool valid = live && tile_rect(p, bbox, layer, r);
+    // binning
     uint32_t npairs = 0;
     if (p.bin_cap) {
-        // fast path: every tile owns bin_cap slots; a tile that needs more flags the render, which is then redone on the
-        // exact count -> alloc -> fill path
+        // fast path: a tile that needs more than bin_cap slots flags the render, which is then redone on the exact
+        // count -> alloc -> fill path
         bool over = false;
-        const uint32_t nt = valid ? r.ntx * r.nty : 0u;
         if (valid && nt <= 8u) {
-            // small primitives: all atomics first, then all stores, so the round trips overlap instead of chaining
-            uint32_t tl[8], sl[8];
             uint32_t jj = 0, ii = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if ((uint32_t)k < nt) {
-                    tl[k] = r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii;
-                    sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
+                    const uint32_t tile = r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii;
+                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + sl[k]] = tri; else over = true;
                     if (++ii == r.ntx) { ii = 0; ++jj; }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if ((uint32_t)k < nt) {
-                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = tri; else over = true;
                 }
             }
             npairs += nt;
@@ -667,6 +675,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy with per-thread addresses (SASS: LDGSTS.E.BYPASS.128)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // -------------------------------------------------------------------------------------------------------
 // K4 / K5: tile raster.
 //
@@ -880,14 +897,9 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
 #undef EUC_PX_TAIL
 }
 
-// sm_100 FADD2: two IEEE f32 additions per issue slot, each half rounded exactly like the scalar instruction.  (Packed
-// multiplies are NOT used anywhere: ptxas contracts a mul.f32x2 that feeds an add.f32x2 into FFMA2 even with .rn and
-// -fmad=false.  In the pixel loop a predicated FADD2 compiles to FADD2 + two selects, which costs more than it saves.)
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
+// Packed f32x2 arithmetic (sm_100 FADD2 / FMUL2) was tried for the chain and rejected: ptxas contracts a mul.f32x2 that
+// feeds an add.f32x2 into FFMA2 even with .rn and -fmad=false (fatal for bit-exactness), a predicated FADD2 compiles to
+// FADD2 + two selects, and the pack / unpack moves of the prefix replay cost more than the saved additions (+2 % time).
 
 // One 16x16 tile, walked by one warp.
 // Not inlined on purpose: inside the persistent loop the register allocation of the (large) tile body got worse.
@@ -1043,12 +1055,32 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         const uint32_t cnt = min(ROUND, n - rd * ROUND);
         const uint32_t cnt0 = min(cnt, (uint32_t)BATCH), cnt1 = cnt - cnt0;
         const uint32_t id0 = batch_id(NB * rd), id1 = cnt1 ? batch_id(NB * rd + 1u) : 0u;
+#ifdef EUC_RECS_TMA
         if (lane == 0) mbar_expect_tx(&bar[0], cnt * SW * 4u);
         __syncwarp();
         if (lane < cnt0) bulk_g2s(recs_sm + lane * SW, p.recs + (size_t)id0 * L::WORDS, SW * 4u, &bar[0]);
         if (NB > 1 && lane < cnt1) bulk_g2s(recs_sm + (BATCH + lane) * SW, p.recs + (size_t)id1 * L::WORDS, SW * 4u, &bar[0]);
         mbar_wait(&bar[0], phase);
         phase ^= 1u;
+#else
+        // Lane t copies record t with 16-byte cp.async (SASS: LDGSTS, no register staging).  One bulk (TMA) copy per
+        // record was measured first: UBLKCP takes uniform-register addresses, so 32 per-lane copies compile to a
+        // 9-instruction elect / broadcast / issue loop per record (5.3 % of the kernel's instructions on C4).
+        if (lane < cnt0) {
+            const uint32_t* src = p.recs + (size_t)id0 * L::WORDS;
+            uint32_t* dst = recs_sm + lane * SW;
+#pragma unroll
+            for (uint32_t k = 0; k < SW / 4u; ++k) cp_async16(dst + 4u * k, src + 4u * k);
+        }
+        if (NB > 1 && lane < cnt1) {
+            const uint32_t* src = p.recs + (size_t)id1 * L::WORDS;
+            uint32_t* dst = recs_sm + (BATCH + lane) * SW;
+#pragma unroll
+            for (uint32_t k = 0; k < SW / 4u; ++k) cp_async16(dst + 4u * k, src + 4u * k);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+#endif
         const uint32_t* stage = recs_sm;
         // the PTX pixel loop (px_step) covers the common case; a round in which any record needs the per-fragment z clip
         // (:271: some vertex failed the clip test), and every other depth mode, takes the general loops
@@ -1267,19 +1299,8 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 float w2 = (q0.z + q2.x * yf) + dx2 * r0f;
                 if (segx0 > r0) {
                     const uint32_t npre = segx0 - r0;
-#ifdef EUC_PX_F32X2
-                    unsigned long long w01 = pack_f32x2(w0, w1);
-                    const unsigned long long dx01 = pack_f32x2(dx0, dx1);
-#pragma unroll 4
-                    for (uint32_t i = 0; i < npre; ++i) {
-                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(w01) : "l"(dx01));
-                        w2 = w2 + dx2;
-                    }
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(w0), "=f"(w1) : "l"(w01));
-#else
 #pragma unroll 4
                     for (uint32_t i = 0; i < npre; ++i) { w0 = w0 + dx0; w1 = w1 + dx1; w2 = w2 + dx2; }
-#endif
                 }
                 const float z0 = q2.y, z1 = q2.z, z2 = q2.w;
                 const float4 q5 = rec4[5];  // flags draw tri -
