@@ -5,11 +5,13 @@
 //                               population count.  One thread per triangle; emits a fixed-size setup record.
 //   K3     alloc_tiles_kernel   gives every non-empty 16x16 tile a private slice of the pair list
 //          fill_kernel          writes (tile <- triangle) pairs
-//   K4/K5  raster_kernel<P>     one warp per tile; restores submission order inside the tile's list (pipeline.rs:581), then: lane = half a tile row (8 px); colour and depth of the tile live
-//                               in registers for the whole list; setup records stream into shared memory through
-//                               cp.async.bulk + mbarrier; coverage, depth test, fragment shade (incl. euc's
+//   K4/K5  raster_kernel<P>     one warp per tile; restores submission order inside the tile's list (pipeline.rs:581),
+//                               then: lane = half a tile row (8 px); depth (and the winner id) of the tile live in
+//                               registers, colour in shared memory, for the whole list; setup records are staged in
+//                               shared memory with cp.async; coverage, depth test, fragment shade (incl. euc's
 //                               coarse-shading "MSAA"), blend in submission order (triangles.rs:219-303,
 //                               pipeline.rs:514-578).
+//          resolve_kernel<P>    deferred pipelines: fragment + blend once per pixel for the winning primitive
 //   K7     fill_u32_kernel      Target::clear (buffer.rs:213-218)
 //
 // Bit-exactness notes (DESIGN.md §"Exactness"): the per-pixel weights are euc's *sequentially accumulated* chain
