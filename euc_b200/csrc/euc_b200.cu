@@ -209,14 +209,21 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
         ctx->stats_on_device = true;
         { StageTimer t(ctx, EUC_STAGE_RASTER); ops.raster(prm, msaa, pblocks, n_tiles); }
         if (resolve) {
-            const uint32_t rows = std::min(prm.row_end, prm.h) - prm.row_begin;
-            const uint32_t px_per_cta_row = msaa ? 64u : 32u;  // resolve_kernel: 2 pixels per thread with MSAA
-            const uint64_t nblocks = (uint64_t)((prm.w + px_per_cta_row - 1) / px_per_cta_row) * ((rows + 3) / 4) * prm.layers;
+            const uint32_t row_end = std::min(prm.row_end, prm.h), rows = row_end - prm.row_begin;
+            uint64_t nblocks;
+            if (msaa) {  // resolve_kernel<MSAA>: one thread per cell of the shading grid, CTAs of 32 x 4 cells (same arithmetic as the kernel)
+                const uint32_t cs = 1u << prm.msaa_level;
+                const uint32_t cells_x = (prm.w + cs - 1) >> prm.msaa_level, cells_per_band = (prm.group_rows + cs - 1) >> prm.msaa_level;
+                const uint32_t bands = rows ? (row_end - 1) / prm.group_rows - prm.row_begin / prm.group_rows + 1 : 0u;
+                nblocks = (uint64_t)((cells_x + 31) / 32) * (((uint64_t)bands * cells_per_band + 3) / 4) * prm.layers;
+            } else {
+                nblocks = (uint64_t)((prm.w + 31) / 32) * ((rows + 3) / 4) * prm.layers;
+            }
             // light shaders: grid-stride over a machine-sized grid (most blocks hold no winner); heavy MSAA shading: one CTA
             // per block so that the hardware balances the expensive blocks dynamically
-            const uint32_t grid = msaa ? (uint32_t)nblocks : (uint32_t)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 16);
+            const uint32_t grid = msaa ? (uint32_t)std::min<uint64_t>(nblocks, 0x7fffffffull) : (uint32_t)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 16);
             StageTimer t(ctx, EUC_STAGE_RESOLVE);
-            ops.resolve(prm, msaa, grid);
+            if (grid > 0) ops.resolve(prm, msaa, grid);
         }
     };
     auto fetch_counters = [&]() -> int {

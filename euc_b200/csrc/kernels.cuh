@@ -1519,31 +1519,28 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
 // One thread per pixel, 32x4-pixel CTAs: rows of a warp are contiguous, so winner loads and colour stores coalesce,
 // and the whole GPU shades in parallel instead of one warp per tile.
 // -------------------------------------------------------------------------------------------------------
-// PXT = pixels per thread along x: 2 with MSAA (pixels 2i and 2i+1 have the same `x >> level` for every level >= 1, so
-// they share all four shading-grid corners when they belong to the same primitive and the corner cache computes them
-// once), 1 otherwise.
+// Without MSAA: one thread per pixel.  With MSAA a thread owns one cell of euc's shading grid (2^L x 2^L pixels whose four
+// corners coincide: tgt_min + (pos << L), anchored at x = 0 and at the first row of the euc band, pipeline.rs:544-551);
+// while the winning primitive stays the same the four corner fragments are shaded once for the whole cell (the
+// reference memoises them per primitive and corner in `fragment_cache`, so this is the same value, not an approximation).
+// Cells never straddle a band: the last cell row of a band is cut at the band's end.
 template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
-    constexpr uint32_t PXT = MSAA ? 2u : 1u;
     if (render_aborted(p)) return;
-    // grid-stride over blocks of (32*PXT) x 4 pixels: most blocks of a frame hold no winner at all, so the grid is sized
-    // by the machine and a CTA just moves on
-    const uint32_t bw = 32u * PXT, nbx = (p.w + bw - 1u) / bw;
-    const uint32_t rows = min(p.row_end, p.h) - p.row_begin, nby = (rows + 3u) / 4u;
-    const uint32_t nblocks = nbx * nby * p.layers;
-    for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const uint32_t layer = blk / (nbx * nby), b2 = blk - layer * nbx * nby, by = b2 / nbx, bx = b2 - by * nbx;
-        const uint32_t x0 = (bx * 32u + (threadIdx.x & 31u)) * PXT;
-        const uint32_t y = p.row_begin + by * 4u + (threadIdx.x >> 5);
-        if (x0 >= p.w || y >= p.h || y >= p.row_end) continue;
-        const size_t row = (size_t)layer * p.w * p.h + (size_t)y * p.w;
-        CornerCache lc, rc;
-        lc.tri = rc.tri = NO_WINNER;
-#pragma unroll
-        for (uint32_t k = 0; k < PXT; ++k) {
-            const uint32_t x = x0 + k;
-            if (x >= p.w) break;
-            const size_t idx = row + x;
+    const uint32_t row_end = min(p.row_end, p.h);
+    if (row_end <= p.row_begin) return;
+    if constexpr (!MSAA) {
+        // grid-stride over blocks of 32 x 4 pixels: most blocks of a frame hold no winner at all, so the grid is sized by
+        // the machine and a CTA just moves on
+        const uint32_t nbx = (p.w + 31u) / 32u;
+        const uint32_t rows = row_end - p.row_begin, nby = (rows + 3u) / 4u;
+        const uint32_t nblocks = nbx * nby * p.layers;
+        for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const uint32_t layer = blk / (nbx * nby), b2 = blk - layer * nbx * nby, by = b2 / nbx, bx = b2 - by * nbx;
+            const uint32_t x = bx * 32u + (threadIdx.x & 31u);
+            const uint32_t y = p.row_begin + by * 4u + (threadIdx.x >> 5);
+            if (x >= p.w || y >= row_end) continue;
+            const size_t idx = (size_t)layer * p.w * p.h + (size_t)y * p.w + x;
             const uint32_t win = p.winner[idx];
             if (win == NO_WINNER) {
                 if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
@@ -1556,15 +1553,77 @@ template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128)
             const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)win * L::WORDS);
             const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
             float frag[4];
-            if (!MSAA) {
-                shade_at<P, LINES>(u, p.samp, rec, (float)x, (float)y, frag);
-            } else {
-                const uint32_t band_lo = (y / p.group_rows) * p.group_rows;
-                msaa_fragment<P, LINES>(u, p.samp, rec, win, x, y, band_lo, p.msaa_level, lc, rc, frag);
-            }
+            shade_at<P, LINES>(u, p.samp, rec, (float)x, (float)y, frag);
             const uint32_t out = P::blend(p.pixel[idx], frag);
             p.pixel[idx] = out;
             for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = out;
+        }
+    } else {
+        // one CTA per block of 32 x 4 cells (the host sizes the grid): the hardware balances the expensive blocks
+        const uint32_t Lv = p.msaa_level, cs = 1u << Lv;
+        const uint32_t cells_x = (p.w + cs - 1u) >> Lv;
+        const uint32_t cells_per_band = (p.group_rows + cs - 1u) >> Lv;
+        const uint32_t band_first = p.row_begin / p.group_rows, band_last = (row_end - 1u) / p.group_rows;  // bands touching the rendered rows
+        const uint32_t cell_rows = (band_last - band_first + 1u) * cells_per_band;
+        const uint32_t nbx = (cells_x + 31u) / 32u, nby = (cell_rows + 3u) / 4u;
+        const uint32_t nblocks = nbx * nby * p.layers;
+        for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const uint32_t layer = blk / (nbx * nby), b2 = blk - layer * nbx * nby, by = b2 / nbx, bx = b2 - by * nbx;
+            const uint32_t cxi = bx * 32u + (threadIdx.x & 31u), cr = by * 4u + (threadIdx.x >> 5);
+            if (cxi >= cells_x || cr >= cell_rows) continue;
+            const uint32_t band = band_first + cr / cells_per_band, kc = cr % cells_per_band;
+            const uint32_t band_lo = band * p.group_rows, band_hi = min(band_lo + p.group_rows, p.h);
+            const uint32_t ya = max(band_lo + (kc << Lv), p.row_begin), yb = min(min(band_lo + ((kc + 1u) << Lv), band_hi), row_end);
+            const uint32_t xa = cxi << Lv, xb = min(xa + cs, p.w);
+            const size_t lay = (size_t)layer * p.w * p.h;
+            if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
+                for (uint32_t y = ya; y < yb; ++y)
+                    for (uint32_t x = xa; x < xb; ++x) {
+                        const size_t idx = lay + (size_t)y * p.w + x;
+                        if (p.winner[idx] == NO_WINNER) {
+                            const uint32_t c = p.pixel[idx];
+                            for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
+                        }
+                    }
+            }
+            // One round per distinct winning primitive of the cell (almost always one).  The four corner shades of a
+            // round are issued before the pixel loop, so the threads of a warp run them together: shading a second
+            // primitive at whatever pixel it first appears left 12 of 32 lanes active in the shader (ncu).
+            const float cx0 = (float)xa, cx1 = (float)(xa + cs);
+            const float cy0 = (float)(band_lo + (kc << Lv)), cy1 = (float)(band_lo + ((kc + 1u) << Lv));
+            const float msaa_div = 1.0f / (float)cs;
+            for (;;) {
+                uint32_t cur = NO_WINNER;
+                for (uint32_t y = ya; y < yb && cur == NO_WINNER; ++y)
+                    for (uint32_t x = xa; x < xb && cur == NO_WINNER; ++x) cur = p.winner[lay + (size_t)y * p.w + x];
+                if (cur == NO_WINNER) break;
+                const float* rec = reinterpret_cast<const float*>(p.recs + (size_t)cur * L::WORDS);
+                const typename P::Uniforms& u = uniforms_of<P>(p, __float_as_uint(rec[R_DRAW]));
+                float t00[4], t01[4], t10[4], t11[4];  // fragments at (cx0, cy0), (cx0, cy1), (cx1, cy0), (cx1, cy1): pipeline.rs:552-561
+                shade_corner<P, LINES>(&u, p.samp, rec, cx0, cy0, t00);
+                shade_corner<P, LINES>(&u, p.samp, rec, cx0, cy1, t01);
+                shade_corner<P, LINES>(&u, p.samp, rec, cx1, cy0, t10);
+                shade_corner<P, LINES>(&u, p.samp, rec, cx1, cy1, t11);
+                for (uint32_t y = ya; y < yb; ++y) {
+                    const float fracty = r_fract((float)(y - band_lo) * msaa_div), omy = 1.0f - fracty;
+                    for (uint32_t x = xa; x < xb; ++x) {
+                        const size_t idx = lay + (size_t)y * p.w + x;
+                        if (p.winner[idx] != cur) continue;
+                        p.winner[idx] = NO_WINNER;  // leave the buffer clean for the next render
+                        const float fractx = r_fract((float)x * msaa_div), omx = 1.0f - fractx;
+                        float frag[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float t0 = t00[c] * omy + t01[c] * fracty;  // weighted_sum2(t00, t01, 1-fy, fy)  :562-570
+                            const float t1 = t10[c] * omy + t11[c] * fracty;  // weighted_sum2(t10, t11, 1-fy, fy)
+                            frag[c] = t0 * omx + t1 * fractx;                 // weighted_sum2(t0, t1, 1-fx, fx)
+                        }
+                        const uint32_t out = P::blend(p.pixel[idx], frag);
+                        p.pixel[idx] = out;
+                        for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = out;
+                    }
+                }
+            }
         }
     }
 }
