@@ -211,6 +211,96 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 // 32 consecutive primitives' records are contiguous in global memory, so the store is fully coalesced, whereas
 // per-thread 16-byte pieces of 144-byte records touch ~22 sectors per request.
 // -------------------------------------------------------------------------------------------------------
+// -------------------------------------------------------------------------------------------------------
+// Fast-path binning of primitives that cover many tiles (fixed-capacity bins: slot = atomicAdd(count), list[slot] = id).
+// An append is a round trip to L2 followed by a dependent store, so a walk costs the round trips it serialises, not
+// the tiles it visits: both walks below issue eight appends per thread before they consume the first slot.
+// -------------------------------------------------------------------------------------------------------
+// Warp level: the (primitive, tile) pairs of the warp's primitives are flattened; item f belongs to the lane whose
+// inclusive prefix is the first one above f, and the 32 lanes take 256 items per round whatever the primitives' sizes.
+// Must be reached by all 32 lanes.
+__device__ __forceinline__ void bin_big_warp(const Params& p, bool big, const TileRect& r, uint32_t nt, uint32_t tri, bool& over, uint32_t& npairs) {
+    const uint32_t lane = threadIdx.x & 31u, full = 0xffffffffu;
+    const uint32_t n = big ? nt : 0u;
+    uint32_t incl = n;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const uint32_t v = __shfl_up_sync(full, incl, s); if (lane >= (uint32_t)s) incl += v; }
+    const uint32_t excl = incl - n, total = __shfl_sync(full, incl, 31);
+    if (total == 0u) return;
+    npairs += n;
+    for (uint32_t base = 0; base < total; base += 256u) {
+        uint32_t tl[8], sl[8], id[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t f = base + (uint32_t)k * 32u + lane;
+            uint32_t j = 0;  // number of lanes whose inclusive prefix is <= f == the owner of item f (32 when f >= total)
+#pragma unroll
+            for (uint32_t st = 16; st > 0; st >>= 1) { if (__shfl_sync(full, incl, (j + st - 1u) & 31u) <= f) j += st; }
+            j &= 31u;
+            const uint32_t l = f - __shfl_sync(full, excl, j), ntx = max(__shfl_sync(full, r.ntx, j), 1u);
+            const uint32_t tx0 = __shfl_sync(full, r.tx0, j), ty0 = __shfl_sync(full, r.ty0, j), lb = __shfl_sync(full, r.layer_base, j);
+            const uint32_t row = l / ntx, col = l - row * ntx;
+            tl[k] = lb + (ty0 + row) * p.tiles_x + tx0 + col;
+            id[k] = tri - lane + j;  // lanes hold consecutive primitives
+            sl[k] = 0u;
+            if (f < total) sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (base + (uint32_t)k * 32u + lane < total) {
+                if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = id[k]; else over = true;
+            }
+        }
+    }
+}
+
+// CTA level, for the few primitives that cover more than 256 tiles (a cube face at 1080p covers thousands): up to 32 of
+// them per CTA are walked by all its threads, one primitive after the other.  Returns true for a lane whose primitive
+// was taken.  Must be reached by every thread of the CTA.
+__device__ __forceinline__ bool bin_huge_cta(const Params& p, bool huge, const TileRect& r, uint32_t nt, uint32_t tri, bool& over, uint32_t& npairs) {
+    constexpr uint32_t HUGE_SLOTS = 32;
+    __shared__ uint32_t huge_n;
+    __shared__ uint4 huge_a[HUGE_SLOTS];  // tx0, ty0, ntx, nt
+    __shared__ uint2 huge_b[HUGE_SLOTS];  // layer_base, tri
+    if (threadIdx.x == 0) huge_n = 0u;
+    __syncthreads();
+    if (huge) {
+        const uint32_t k = atomicAdd(&huge_n, 1u);
+        if (k < HUGE_SLOTS) {
+            huge_a[k] = make_uint4(r.tx0, r.ty0, r.ntx, nt);
+            huge_b[k] = make_uint2(r.layer_base, tri);
+            npairs += nt;
+        } else {
+            huge = false;
+        }
+    }
+    __syncthreads();
+    const uint32_t hn = min(huge_n, HUGE_SLOTS);
+    for (uint32_t e = 0; e < hn; ++e) {
+        const uint4 a = huge_a[e];
+        const uint2 b = huge_b[e];
+        for (uint32_t base = 0; base < a.w; base += 8u * blockDim.x) {
+            uint32_t tl[8], sl[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t i = base + (uint32_t)k * blockDim.x + threadIdx.x;
+                const uint32_t row = i / a.z, col = i - row * a.z;
+                tl[k] = b.x + (a.y + row) * p.tiles_x + a.x + col;
+                sl[k] = 0u;
+                if (i < a.w) sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (base + (uint32_t)k * blockDim.x + threadIdx.x < a.w) {
+                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = b.y; else over = true;
+                }
+            }
+        }
+    }
+    return huge;
+}
+
+constexpr uint32_t SETUP_LOCAL_TILES = 32;  // primitives covering up to this many tiles are binned by their own thread
 template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
     __shared__ __align__(128) uint32_t rec_stage[128][L::WORDS];
@@ -305,9 +395,10 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         p.tri_bbox[tri] = bbox;
         valid = tile_rect(p, bbox, layer, r);
         nt = valid ? r.ntx * r.nty : 0u;
-        if (p.bin_cap && valid && nt <= 8u) {
-            // fast path, small primitives: every tile owns bin_cap slots; all appends are issued back to back so that their
-            // round trips overlap, and the slots are consumed after the record has been written
+        if (p.bin_cap && valid && nt <= SETUP_LOCAL_TILES) {
+            // fast path, primitives binned by their own thread: every tile owns bin_cap slots; the appends of (the first)
+            // eight tiles are issued back to back so that their round trips overlap, and the slots are consumed after the
+            // record has been written
             uint32_t jj = 0, ii = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -405,23 +496,35 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         // fast path: a tile that needs more than bin_cap slots flags the render, which is then redone on the exact
         // count -> alloc -> fill path
         bool over = false;
-        if (valid && nt <= 8u) {
+        if (valid && nt <= SETUP_LOCAL_TILES) {
+            // chunks of eight tiles: all appends of a chunk, then all its stores (the first chunk's appends were issued above).
+            // A warp-cooperative walk (below) serialises its 32 primitives on the append round trip; with teapot-sized
+            // triangles (9 .. 32 tiles at 4K) that made the whole setup kernel three times longer.
             uint32_t jj = 0, ii = 0;
+            for (uint32_t k0 = 0; k0 < nt; k0 += 8u) {
+                uint32_t tl[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if ((uint32_t)k < nt) {
-                    const uint32_t tile = r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii;
-                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + sl[k]] = tri; else over = true;
-                    if (++ii == r.ntx) { ii = 0; ++jj; }
+                for (int k = 0; k < 8; ++k) {
+                    if (k0 + (uint32_t)k < nt) {
+                        tl[k] = r.layer_base + (r.ty0 + jj) * p.tiles_x + r.tx0 + ii;
+                        if (k0) sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
+                        if (++ii == r.ntx) { ii = 0; ++jj; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k0 + (uint32_t)k < nt) {
+                        if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = tri; else over = true;
+                    }
                 }
             }
             npairs += nt;
         }
-        for_each_tile(p, valid && nt > 8u, r, tri, [&](uint32_t tile, uint32_t t) {
-            const uint32_t slot = atomicAdd(p.tile_count + tile, 1u);
-            if (slot < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + slot] = t; else over = true;
-            ++npairs;
-        });
+        bool big = valid && nt > SETUP_LOCAL_TILES;
+        if (p.cta_bin) {  // uniform: the host enables it for renders with few primitives (barriers cost ~15 us at 2^20)
+            if (bin_huge_cta(p, big && nt > 256u, r, nt, tri, over, npairs)) big = false;
+        }
+        bin_big_warp(p, big, r, nt, tri, over, npairs);
         if (over) atomicOr(p.counters + 3, 2ull);
     } else {
         for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
