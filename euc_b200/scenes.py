@@ -209,4 +209,4 @@ def voxel_icon_batch(n_icons, first_icon=0):
         ibase += i.size
         mvp = voxel_icon_mvp(first_icon + k)
         ubs.append(np.ascontiguousarray(mvp.T).tobytes() + np.append(VOXEL_LIGHT_DIR, f32(0)).astype(f32).tobytes())
-    return np.concatenate(vs), np.concatenate(is_), draws, b"".join(ubs)
+    return np.concatenate(vs), np.concatenate(is_), np.asarray(draws, dtype=np.int64).reshape(-1, 4), b"".join(ubs)
