@@ -53,6 +53,7 @@ struct euc_ctx {
     unsigned long long* counters = nullptr;      // device, 8 words: pairs, fragments, list cursor, flags, tile ticket
     unsigned long long* counters_host = nullptr;  // pinned
     bool stats = false;
+    int sparse_recs = -1;  // EUC_SPARSE_RECS (development): -1 = automatic, 0 / 1 = force
     euc_render_stats last{};
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
     int sm_count = 148;
@@ -185,16 +186,13 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     const bool msaa = prm.msaa_level > 0 && ops.has_fragment && prm.pixel_write;
     const int resident = ops.resident(msaa);  // CTAs of the raster kernel that fit one SM (sets its smem attribute once)
     if (resident <= 0) return fail(ctx, EUC_E_CUDA, "raster kernel occupancy query failed");
-    // persistent grid: one resident set of CTAs; warps take tiles from a ticket counter (counters[4], zeroed per render)
-    // Balanced: every warp should walk the same number of tiles, otherwise the kernel lasts as long as the unlucky
-    // warps with one tile more (with 1.4 tiles per resident warp that is 2 tile-times instead of 1.4; fewer warps per
-    // SM run proportionally faster on this issue-bound kernel, so nothing is lost by launching fewer).
+    // persistent grid: one resident set of CTAs (or one warp per tile if there are fewer tiles); warps take tiles from a
+    // ticket counter (counters[4], zeroed per render).  A "balanced" grid (every warp the same number of tiles, fewer warps)
+    // was measured against this with the 6-CTA kernel and lost at every size: 3 % on the full C4 frame, 9 % on one eighth
+    // of it (tools/band_probe.py): early finishers that pick up the remaining tiles run them at low occupancy, i.e. fast.
     const uint32_t ty_lo = prm.row_begin / TILE, ty_hi = (std::min(prm.row_end, prm.h) + TILE - 1) / TILE;
     const uint64_t n_active = (uint64_t)(ty_hi - ty_lo) * prm.tiles_x * prm.layers;
-    const uint64_t max_warps = (uint64_t)ctx->sm_count * resident * RASTER_WARPS;
-    const uint64_t tiles_per_warp = std::max<uint64_t>(1, (n_active + max_warps - 1) / max_warps);
-    const uint64_t want_warps = (n_active + tiles_per_warp - 1) / tiles_per_warp;
-    const uint32_t pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((want_warps + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
+    const uint32_t pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_active + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
     (void)rblocks;
     const bool resolve = ops.defer && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
     if (resolve) {
@@ -465,6 +463,9 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     prm.cull = d.cull_mode; prm.flip_y = d.y_axis_up ? -1.0f : 1.0f;
     prm.prim_kind = d.primitive_kind;
     prm.cta_bin = tri_total <= 65536 ? 1u : 0u;
+    // row-restricted renders (multi-GPU bands) that keep less than half of the rows: most records are dropped, so the live
+    // ones are stored by their own lanes instead of one bulk store per warp that would write all 32 slots
+    prm.sparse_recs = ctx->sparse_recs >= 0 ? (uint32_t)ctx->sparse_recs : ((uint64_t)(prm.row_end - prm.row_begin) * 2 < prm.h ? 1u : 0u);
     prm.vertices = rc.geom->verts; prm.vstride = rc.geom->stride; prm.n_vertices = rc.geom->n_verts;
     prm.indices = rc.geom->idx;
     prm.n_draws = rc.n_draws; prm.n_tris = (uint32_t)tri_total;
@@ -566,6 +567,7 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
         cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
+    if (const char* e = getenv("EUC_SPARSE_RECS")) ctx->sparse_recs = atoi(e);
     *out_ctx = ctx;
     return EUC_OK;
 }

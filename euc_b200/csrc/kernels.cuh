@@ -89,6 +89,7 @@ struct Params {
     uint32_t list_capacity;
     int32_t prim_kind;      // euc_primitive_kind
     uint32_t cta_bin;       // 1: primitives covering > 256 tiles are binned by the whole CTA (few, huge primitives)
+    uint32_t sparse_recs;   // 1: live records are stored by their own lanes (row-restricted renders drop most primitives)
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
     int32_t stats;
@@ -301,7 +302,10 @@ __device__ __forceinline__ bool bin_huge_cta(const Params& p, bool huge, const T
 }
 
 constexpr uint32_t SETUP_LOCAL_TILES = 32;  // primitives covering up to this many tiles are binned by their own thread
-template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __grid_constant__ Params p) {
+#ifndef EUC_SETUP_MIN_CTAS
+#define EUC_SETUP_MIN_CTAS 1
+#endif
+template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) setup_kernel(const __grid_constant__ Params p) {
     using L = RecLayout<P>;
     __shared__ __align__(128) uint32_t rec_stage[128][L::WORDS];
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,7 +483,14 @@ template <class P> __global__ void __launch_bounds__(128) setup_kernel(const __g
         }
     }
     if (__any_sync(0xffffffffu, oob) && oob) atomicOr(p.counters + 3, 1ull);
-    {   // one bulk store per warp: records of primitives [warp_first, warp_first + nrec)
+    if (p.sparse_recs) {  // uniform
+        if (bbox.x | bbox.y) {
+            const float4* src = reinterpret_cast<const float4*>(rec_stage[threadIdx.x]);
+            float4* dst = reinterpret_cast<float4*>(p.recs + (size_t)tri * L::WORDS);
+#pragma unroll
+            for (int k = 0; k < L::WORDS / 4; ++k) dst[k] = src[k];
+        }
+    } else {   // one bulk store per warp: records of primitives [warp_first, warp_first + nrec)
         const uint32_t warp_first = tri - (threadIdx.x & 31u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above, async-proxy read below
         __syncwarp();

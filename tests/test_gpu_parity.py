@@ -280,6 +280,26 @@ def test_quirks_and_errors():
     assert_depth_bit_exact(z.raw(), rz, "partial primitive")
 
 
+def test_many_small_and_a_few_screen_sized_primitives():
+    """More than 65536 primitives switch the CTA-cooperative bin walk off; screen-sized primitives among them then go through
+    the flattened per-warp walk (thousands of tiles per primitive), medium ones through the chunked per-thread walk."""
+    w, h = 1024, 512
+    small = _random_tris(66000, 0xB16, size=0.01).reshape(-1, 3)
+    big = np.zeros((4, 3), dtype=e.VERTEX_P4C4)
+    big["pos"][0] = [(-1, -1, 0.9, 1), (1, -1, 0.9, 1), (0, 1, 0.9, 1)]
+    big["pos"][1] = [(-1.5, -1.2, 0.5, 1), (1.5, -0.9, 0.5, 1), (-1.4, 1.3, 0.5, 1)]
+    big["pos"][2] = [(-0.3, -0.3, 0.2, 1), (0.4, -0.2, 0.2, 1), (0.0, 0.5, 0.2, 1)]   # ~150 tiles
+    big["pos"][3] = [(-0.1, -0.1, 0.1, 1), (0.1, -0.1, 0.1, 1), (0.0, 0.1, 0.1, 1)]   # ~20 tiles
+    big["rgba"][:, :, :3] = [[(1, 0, 0)], [(0, 1, 0)], [(0, 0, 1)], [(1, 1, 0)]]
+    big["rgba"][:, :, 3] = 0.5
+    verts = np.concatenate([small[:20000], big[:2], small[20000:40000], big[2:], small[40000:]]).reshape(-1)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), verts, w, h, clear_px=0xFF000000)
+    assert_depth_bit_exact(gz, rz, "small + screen-sized")
+    assert_colour_within_1lsb(gpx, rpx, "small + screen-sized")
+    assert gs["fragments"] == rs["fragments"]
+    assert gs["primitives"] == 66004
+
+
 def test_pair_list_overflow_relaunch():
     """A fresh context sizes the (tile, primitive) list optimistically; full-screen triangles overflow that guess, the
     device flags it, and the host re-launches fill + raster after growing the list.  Results must be unaffected."""
