@@ -192,7 +192,15 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     // of it (tools/band_probe.py): early finishers that pick up the remaining tiles run them at low occupancy, i.e. fast.
     const uint32_t ty_lo = prm.row_begin / TILE, ty_hi = (std::min(prm.row_end, prm.h) + TILE - 1) / TILE;
     const uint64_t n_active = (uint64_t)(ty_hi - ty_lo) * prm.tiles_x * prm.layers;
-    const uint32_t pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_active + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
+    uint32_t pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_active + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
+    if (prm.n_mirrors) {
+        // fused gather (peer stores over NVLink at every tile's write-back): here the balanced grid wins (N = 8: raster
+        // 0.133 vs 0.149 ms) because fewer warps finish their tiles, and burst their rows onto the links, at the same time
+        const uint64_t max_warps = (uint64_t)ctx->sm_count * resident * RASTER_WARPS;
+        const uint64_t tiles_per_warp = std::max<uint64_t>(1, (n_active + max_warps - 1) / max_warps);
+        const uint64_t want_warps = (n_active + tiles_per_warp - 1) / tiles_per_warp;
+        pblocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((want_warps + RASTER_WARPS - 1) / RASTER_WARPS, (uint64_t)ctx->sm_count * resident));
+    }
     (void)rblocks;
     const bool resolve = ops.defer && prm.pixel_write;  // deferred pipelines: raster records winners, resolve_kernel shades
     if (resolve) {
