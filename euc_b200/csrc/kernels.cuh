@@ -964,7 +964,7 @@ __device__ __forceinline__ void msaa_fragment(const typename P::Uniforms& u, con
 // Every f32 operation carries .rn and is therefore never contracted; operation order is the reference's.
 //   d     sgn*depth of pixel J (register)        mask  bit J set when the fragment passed
 //   w0..2 chain values at pixel J, advanced to J+1 when J >= jlo       [jlo, jhi) pixels of the segment inside row_range
-template <int J, bool DEFER>
+template <int J, bool DEFER, bool GREATER>
 __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, float& w1, float& w2, uint32_t& mask, const float dx0,
                                         const float dx1, const float dx2, const float z0, const float z1, const float z2, const float dsgn,
                                         const uint32_t jlo, const uint32_t jhi, const uint32_t tri) {
@@ -988,7 +988,7 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
     "add.rn.f32 z, z, t;\n"                                                                                             \
     "mul.rn.f32 t, %11, wu;\n"                                                                                          \
     "add.rn.f32 z, z, t;\n"                /* :269 z = z0*w0 + z1*w1 + z2*wu */                                          \
-    "mul.rn.f32 z, z, %12;\n"              /* sgn-space (exact) */                                                       \
+    EUC_PX_SGN                             /* GREATER keeps -depth in the registers: negate z (exact) */                 \
     EUC_PX_MIN3                            /* all three >= 0 (:267); NaN in any weight fails like the three compares */  \
     "setp.ge.and.f32 pp, m, 0f00000000, pp;\n"                                                                          \
     "setp.lt.and.f32 pp, z, %0, pp;\n"     /* pipeline.rs:519-526 */                                                     \
@@ -1002,10 +1002,16 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
 #define EUC_PX_OPERANDS                                                                                                 \
     : "+f"(d), "+f"(w0), "+f"(w1), "+f"(w2), "+r"(mask), "+r"(cwj)                                                      \
     : "f"(dx0), "f"(dx1), "f"(dx2), "f"(z0), "f"(z1), "f"(z2), "f"(dsgn), "r"(jlo), "r"(jhi), "n"(J), "n"(1 << J), "r"(tri)
-    if constexpr (DEFER) {
-        asm(EUC_PX_BODY "@pp mov.b32 %5, %17;\n" EUC_PX_TAIL EUC_PX_OPERANDS);
+    if constexpr (GREATER) {
+#define EUC_PX_SGN "neg.f32 z, z;\n"
+        if constexpr (DEFER) asm(EUC_PX_BODY "@pp mov.b32 %5, %17;\n" EUC_PX_TAIL EUC_PX_OPERANDS);
+        else asm(EUC_PX_BODY EUC_PX_TAIL EUC_PX_OPERANDS);
+#undef EUC_PX_SGN
     } else {
-        asm(EUC_PX_BODY EUC_PX_TAIL EUC_PX_OPERANDS);
+#define EUC_PX_SGN
+        if constexpr (DEFER) asm(EUC_PX_BODY "@pp mov.b32 %5, %17;\n" EUC_PX_TAIL EUC_PX_OPERANDS);
+        else asm(EUC_PX_BODY EUC_PX_TAIL EUC_PX_OPERANDS);
+#undef EUC_PX_SGN
     }
 #undef EUC_PX_OPERANDS
 #undef EUC_PX_BODY
@@ -1436,14 +1442,25 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 }
 #endif
                 if (fast_px) {  // warp-uniform: LESS / GREATER with depth write, no record of this round needs the z clip
-                    px_step<0, DEFER>(depth[0], cw[0], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<1, DEFER>(depth[1], cw[1], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<2, DEFER>(depth[2], cw[2], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<3, DEFER>(depth[3], cw[3], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<4, DEFER>(depth[4], cw[4], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<5, DEFER>(depth[5], cw[5], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<6, DEFER>(depth[6], cw[6], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
-                    px_step<7, DEFER>(depth[7], cw[7], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    if (dsgn < 0.0f) {
+                        px_step<0, DEFER, true>(depth[0], cw[0], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<1, DEFER, true>(depth[1], cw[1], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<2, DEFER, true>(depth[2], cw[2], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<3, DEFER, true>(depth[3], cw[3], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<4, DEFER, true>(depth[4], cw[4], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<5, DEFER, true>(depth[5], cw[5], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<6, DEFER, true>(depth[6], cw[6], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<7, DEFER, true>(depth[7], cw[7], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    } else {
+                        px_step<0, DEFER, false>(depth[0], cw[0], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<1, DEFER, false>(depth[1], cw[1], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<2, DEFER, false>(depth[2], cw[2], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<3, DEFER, false>(depth[3], cw[3], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<4, DEFER, false>(depth[4], cw[4], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<5, DEFER, false>(depth[5], cw[5], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<6, DEFER, false>(depth[6], cw[6], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                        px_step<7, DEFER, false>(depth[7], cw[7], w0, w1, w2, passmask, dx0, dx1, dx2, z0, z1, z2, dsgn, jlo, jhi, tri_id);
+                    }
                 } else if (fast_depth) {
                     // z clip as bounds: when every vertex passed the clip the per-fragment test is skipped (:271), i.e.
                     // the bounds are infinite.  A NaN z fails here but would fail the depth comparison anyway.

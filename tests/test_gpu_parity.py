@@ -280,6 +280,49 @@ def test_quirks_and_errors():
     assert_depth_bit_exact(z.raw(), rz, "partial primitive")
 
 
+def _slivers_and_giants(n, seed, w, h):
+    """Stress for the per-row interval test of the tile kernel: near-horizontal and near-vertical slivers that cross the
+    whole target (tiny weight slopes, long accumulation chains), triangles far larger than the screen (weights that
+    nearly cancel at the visible rows), and sub-pixel triangles; perspective on half of them."""
+    r = scenes.u01(seed, n * 12).reshape(n, 12)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    kind = (r[:, 0] * 4).astype(int)
+    x0, y0 = r[:, 1] * 2.4 - 1.2, r[:, 2] * 2.4 - 1.2
+    px, py = 2.0 / w, 2.0 / h
+    ndc = np.zeros((n, 3, 2))
+    # 0: horizontal sliver   1: vertical sliver   2: giant   3: sub-pixel
+    ndc[:, 0] = np.stack([x0, y0], 1)
+    hs = kind == 0
+    ndc[hs, 1] = np.stack([x0 + 2.5 * (r[:, 3] - 0.5) * 2, y0 + (r[:, 4] - 0.5) * 6 * py], 1)[hs]
+    ndc[hs, 2] = np.stack([x0 + 2.5 * (r[:, 5] - 0.5) * 2, y0 + (r[:, 6] - 0.5) * 6 * py], 1)[hs]
+    vs = kind == 1
+    ndc[vs, 1] = np.stack([x0 + (r[:, 3] - 0.5) * 6 * px, y0 + 2.5 * (r[:, 4] - 0.5) * 2], 1)[vs]
+    ndc[vs, 2] = np.stack([x0 + (r[:, 5] - 0.5) * 6 * px, y0 + 2.5 * (r[:, 6] - 0.5) * 2], 1)[vs]
+    gs = kind == 2
+    ndc[gs, 1] = np.stack([x0 + (r[:, 3] - 0.5) * 80, y0 + (r[:, 4] - 0.5) * 80], 1)[gs]
+    ndc[gs, 2] = np.stack([x0 + (r[:, 5] - 0.5) * 80, y0 + (r[:, 6] - 0.5) * 80], 1)[gs]
+    ss = kind == 3
+    ndc[ss, 1] = np.stack([x0 + (r[:, 3] - 0.5) * 3 * px, y0 + (r[:, 4] - 0.5) * 3 * py], 1)[ss]
+    ndc[ss, 2] = np.stack([x0 + (r[:, 5] - 0.5) * 3 * px, y0 + (r[:, 6] - 0.5) * 3 * py], 1)[ss]
+    wv = np.where(r[:, 7:8] < 0.5, 1.0, 0.4 + 2.0 * r[:, 8:11])
+    v["pos"][:, :, 0] = ndc[:, :, 0] * wv
+    v["pos"][:, :, 1] = ndc[:, :, 1] * wv
+    v["pos"][:, :, 2] = (0.05 + 0.9 * r[:, 11:12]) * wv
+    v["pos"][:, :, 3] = wv
+    v["rgba"][:, :, :3] = r[:, None, 8:11]
+    v["rgba"][:, :, 3] = 0.4
+    return v.reshape(-1)
+
+
+@pytest.mark.parametrize("w,h,seed", [(4096, 64, 11), (640, 480, 12), (1920, 1080, 13)])
+def test_slivers_giants_and_subpixel_triangles(w, h, seed):
+    verts = _slivers_and_giants(1500, 0x511 + seed, w, h)
+    gpx, gz, rpx, rz, gs, rs = run_both(lambda t: e.BlendTris(), verts, w, h, clear_px=0xFF000000)
+    assert_depth_bit_exact(gz, rz, f"slivers/giants {w}x{h}")
+    assert_colour_within_1lsb(gpx, rpx, f"slivers/giants {w}x{h}")
+    assert gs["fragments"] == rs["fragments"] > 1000
+
+
 def test_many_small_and_a_few_screen_sized_primitives():
     """More than 65536 primitives switch the CTA-cooperative bin walk off; screen-sized primitives among them then go through
     the flattened per-warp walk (thousands of tiles per primitive), medium ones through the chunked per-thread walk."""
