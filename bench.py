@@ -316,15 +316,13 @@ def run_ours(args, rank, world, local_rank):
             keep.extend([gather, host_out, color, depth, geom, token])
 
             def frame():
+                # clears + render in one call (euc_render_clear: the tile kernels start from the clear values and write
+                # every tile of the rendered rows; same bytes as clear(); clear(); render(), tests/test_fused_clear.py)
                 if fused:
-                    color.clear_rows(0xFF000000, r0, r1)
-                    depth.clear_rows(1.0, r0, r1)
-                    pipe.render(geom, color, depth, rows=(r0, r1), mirrors=mirrors)
+                    pipe.render(geom, color, depth, rows=(r0, r1), mirrors=mirrors, clear=(0xFF000000, 1.0))
                     dist.all_reduce(token)  # stream-ordered barrier: every rank's rows have landed everywhere
                 else:
-                    color.clear(0xFF000000)
-                    depth.clear(1.0)
-                    pipe.render(geom, color, depth, rows=(r0, r1))
+                    pipe.render(geom, color, depth, rows=(r0, r1), clear=(0xFF000000, 1.0))
                     if world > 1:
                         dist.all_gather_into_tensor(gather, my_slot)
 
@@ -389,13 +387,10 @@ def run_ours(args, rank, world, local_rank):
         keep += [pv, host_out]
 
         def frame(count=None):
-            color.clear(0)
-            depth.clear(1.0)
-            shadow.clear(1.0)
-            p1.render(geom, empty, shadow)
+            p1.render(geom, empty, shadow, clear=(None, 1.0))
             if count is not None:
                 count.append(ctx.get_stats()["fragments"])
-            p2.render(geom, color, depth)
+            p2.render(geom, color, depth, clear=(0, 1.0))
 
         def frame_e2e():
             geom.update(pv.data_ptr())
@@ -416,8 +411,7 @@ def run_ours(args, rank, world, local_rank):
         keep += [pv, pi, host_out]
 
         def frame():
-            color.clear(180)
-            pipe.render(geom, color, empty)
+            pipe.render(geom, color, empty, clear=(180, None))
 
         def frame_e2e():
             geom.update(pv.data_ptr(), pi.data_ptr())
@@ -438,9 +432,7 @@ def run_ours(args, rank, world, local_rank):
         keep += [pv, pi, host_out]
 
         def frame():
-            color.clear(0)
-            depth.clear(1.0)
-            pipe.render_batch(geom, scene["draws"], scene["ubs"], color, depth)
+            pipe.render_batch(geom, scene["draws"], scene["ubs"], color, depth, clear=(0, 1.0))
 
         def frame_e2e():
             geom.update(pv.data_ptr(), pi.data_ptr())
@@ -566,7 +558,8 @@ def run_ours(args, rank, world, local_rank):
             "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak" if wl == "c5" else ("strong" if wl == "c4" else "weak"),
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": c["name"], "target": f"{w}x{h}", "frames_per_step": frames_per_step}, **config_extra),
+            "config": dict({"workload": c["name"], "target": f"{w}x{h}", "frames_per_step": frames_per_step,
+                            "clears": "every frame clears its targets; the clears are fused into the render calls (euc_render_clear)"}, **config_extra),
             "mfrag_per_s": frags_per_frame * job_mult * steps / (ms / 1000.0) / 1e6,
             "fragments_per_step": frags_per_frame,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,

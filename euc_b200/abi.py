@@ -64,6 +64,7 @@ SYMBOLS = {
     "euc_buf_destroy": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_buf_clear": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p]),
     "euc_buf_clear_rows": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "euc_render_clear": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "euc_buf_upload": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_buf_download": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "euc_host_alloc": (C.c_int, [_ctx_p, C.c_size_t, C.POINTER(C.c_void_p)]),

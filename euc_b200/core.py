@@ -130,6 +130,13 @@ class Context:
     def sync(self):
         self._check(self._lib.euc_sync(self._p))
 
+    def render_clear(self, pixel_value=None, depth_value=None):
+        """The next render of this context first clears its pixel target to `pixel_value` (u32) and its depth target to
+        `depth_value` (f32), fused into the render's kernels (euc_render_clear)."""
+        pv = C.c_uint32(int(pixel_value) & 0xFFFFFFFF) if pixel_value is not None else None
+        zv = C.c_float(float(depth_value)) if depth_value is not None else None
+        self._check(self._lib.euc_render_clear(self._p, C.byref(pv) if pv is not None else None, C.byref(zv) if zv is not None else None))
+
     def set_stats(self, enabled):
         self._check(self._lib.euc_set_stats(self._p, 1 if enabled else 0))
 
@@ -442,9 +449,11 @@ class Pipeline:
         self._frozen = self.build_desc(lambda s: s.texture.handle)
         return self
 
-    def render(self, vertices, pixel, depth, rows=None, mirrors=None):
+    def render(self, vertices, pixel, depth, rows=None, mirrors=None, clear=None):
         """Pipeline::render (src/pipeline.rs:248).  `vertices`: numpy vertex array (stream), IndexedVertices, or a
-        device-resident Geometry.  `pixel` / `depth`: Buffer2d or Empty().  Asynchronous on the context's stream."""
+        device-resident Geometry.  `pixel` / `depth`: Buffer2d or Empty().  Asynchronous on the context's stream.
+        clear=(pixel_value | None, depth_value | None): same result as `pixel.clear(..); depth.clear(..)` (restricted to
+        `rows`) followed by this render, with the clears fused into the render's kernels (euc_render_clear)."""
         ctx = None
         for t in (pixel, depth, vertices):
             if isinstance(t, (Buffer2d, Geometry)):
@@ -453,6 +462,8 @@ class Pipeline:
         ctx = ctx or default_context()
         d, keep = getattr(self, "_frozen", None) or self.build_desc(lambda s: s.texture.handle)
         lib = ctx._lib
+        if clear is not None:
+            ctx.render_clear(*clear)
         if isinstance(vertices, Geometry):
             if mirrors:
                 r0, r1 = rows if rows is not None else (0, 0xFFFFFFFF)
@@ -475,10 +486,12 @@ class Pipeline:
         if rc:
             ctx._check(rc)
 
-    def render_batch(self, geometry, draws, uniform_blocks, pixel, depth):
+    def render_batch(self, geometry, draws, uniform_blocks, pixel, depth, clear=None):
         """n independent Pipeline::render calls in one launch sequence.  draws: iterable of (first, count,
-        base_vertex, layer); uniform_blocks: bytes of len(draws) uniform blocks."""
+        base_vertex, layer); uniform_blocks: bytes of len(draws) uniform blocks.  clear: as in render()."""
         ctx = geometry.ctx
+        if clear is not None:
+            ctx.render_clear(*clear)
         d, keep = self.build_desc(lambda s: s.texture.handle)
         # draws as one int64 -> 4 x 32-bit table (euc_batch_draw is four 32-bit words); a Python loop over ctypes structs
         # costs ~1 us per draw, which is the GPU time of a whole icon

@@ -53,6 +53,7 @@ struct euc_ctx {
     unsigned long long* counters = nullptr;      // device, 8 words: pairs, fragments, list cursor, flags, tile ticket
     unsigned long long* counters_host = nullptr;  // pinned
     bool stats = false;
+    struct ClearReq { bool px = false, z = false; uint32_t px_value = 0, z_value = 0; } next_clear;  // euc_render_clear: consumed by the next render
     int sparse_recs = -1;  // EUC_SPARSE_RECS (development): -1 = automatic, 0 / 1 = force
     euc_render_stats last{};
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
@@ -166,6 +167,38 @@ struct PipeOps {
     std::function<int(bool msaa)> resident;
 };
 
+// Fills rows [row_begin, row_end) of every layer of a buffer (Target::clear restricted to a row range).
+static int clear_rows_impl(euc_ctx* ctx, const Buf& b, uint32_t v, uint32_t row_begin, uint32_t row_end) {
+    row_end = std::min(row_end, b.h);
+    if (row_begin >= row_end || b.w == 0) return EUC_OK;
+    if (row_begin == 0 && row_end == b.h) {  // whole buffer: one launch over all layers
+        const size_t n = b.bytes / 4, vec = (n + 3) / 4;
+        if (n == 0) return EUC_OK;
+        const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
+        ++ctx->launches;
+        fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)b.d, n, v);
+        CU(cudaGetLastError());
+        return EUC_OK;
+    }
+    for (uint32_t l = 0; l < b.layers; ++l) {
+        uint32_t* base = (uint32_t*)b.d + ((size_t)l * b.h + row_begin) * b.w;
+        const size_t n = (size_t)(row_end - row_begin) * b.w;
+        if (((uintptr_t)base & 15u) != 0) return fail(ctx, EUC_E_UNSUPPORTED, "row range is not 16-byte aligned");
+        const size_t vec = (n + 3) / 4;
+        const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
+        ++ctx->launches;
+        fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>(base, n, v);
+    }
+    CU(cudaGetLastError());
+    return EUC_OK;
+}
+
+// A euc_render_clear request belongs to the next render call only: whatever way that call ends, the request is gone.
+struct DropClear {
+    euc_ctx* ctx;
+    ~DropClear() { if (ctx) ctx->next_clear = euc_ctx::ClearReq{}; }
+};
+
 // Pipeline-agnostic render driver.  `ops` describes the pipeline (record size, flags) and launches its kernels: template
 // instantiations for the built-in pipelines, NVRTC-compiled modules for pipelines registered at run time.
 int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles, const PipeOps& ops) {
@@ -181,6 +214,13 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     if ((rcode = ensure(ctx, ctx->recs, (size_t)prm.n_tris * ops.rec_bytes)) != EUC_OK) return rcode;
     prm.recs = (uint32_t*)ctx->recs.p;
 
+    if ((prm.clear_mask & 1u) && !ops.has_fragment) {
+        // no fragment stage: the tile kernel never touches the colour target, so its clear is a plain fill
+        Buf pxb{}; pxb.d = prm.pixel; pxb.w = prm.w; pxb.h = prm.h; pxb.layers = prm.layers; pxb.bytes = (size_t)prm.w * prm.h * prm.layers * 4;
+        int crc = clear_rows_impl(ctx, pxb, prm.clear_px, prm.row_begin, prm.row_end);
+        if (crc != EUC_OK) return crc;
+        prm.clear_mask &= ~1u;
+    }
     const uint32_t tri_blocks = (prm.n_tris + 127) / 128;
     const uint32_t rblocks = (n_tiles + RASTER_WARPS - 1) / RASTER_WARPS;
     const bool msaa = prm.msaa_level > 0 && ops.has_fragment && prm.pixel_write;
@@ -395,8 +435,6 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     const bool shadow = d.pipeline_id == EUC_PIPE_TEAPOT_SHADOW;
     const bool pixel_write = d.pixel_write != 0;
     const bool uses_depth = d.depth_test != EUC_DEPTH_NONE || d.depth_write != 0;
-    // pipeline.rs:256-270
-    if (!pixel_write && !uses_depth) return EUC_OK;
     const Buf* pb = nullptr;
     const Buf* db = nullptr;
     if (rc.pixel) {
@@ -409,6 +447,18 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
         if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown depth buffer handle");
         db = &it->second;
     }
+    // euc_render_clear: whatever part of the requested clear the kernels of this render do not perform themselves is a
+    // plain fill of the rendered rows, issued before them (also when the render turns out to draw nothing)
+    euc_ctx::ClearReq clr = ctx->next_clear;
+    ctx->next_clear = euc_ctx::ClearReq{};
+    auto plain_clear = [&](bool px, bool z) -> int {
+        int c = EUC_OK;
+        if (px && clr.px && pb) { clr.px = false; if ((c = clear_rows_impl(ctx, *pb, clr.px_value, rc.row_begin, rc.row_end)) != EUC_OK) return c; }
+        if (z && clr.z && db) { clr.z = false; if ((c = clear_rows_impl(ctx, *db, clr.z_value, rc.row_begin, rc.row_end)) != EUC_OK) return c; }
+        return c;
+    };
+    // pipeline.rs:256-270
+    if (!pixel_write && !uses_depth) return plain_clear(true, true);
     uint32_t w = 0, h = 0, layers = 1;
     auto size_of = [](const Buf* b, uint32_t& bw, uint32_t& bh, uint32_t& bl) { bw = b ? b->w : 0; bh = b ? b->h : 0; bl = b ? b->layers : 1; };
     if (pixel_write && uses_depth) {
@@ -423,18 +473,18 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     } else {
         size_of(db, w, h, layers);
     }
-    if (w == 0 || h == 0) return EUC_OK;  // Empty target: size [0,0] -> needed_threads == 0 -> nothing happens
+    if (w == 0 || h == 0) return plain_clear(true, true);  // Empty target: size [0,0] -> needed_threads == 0 -> nothing happens
     const uint32_t msaa = (uint32_t)std::min(std::max(d.msaa_level, 0), 6);  // pipeline.rs:291-294
     // pipeline.rs:329-330.  width > 20000*2^msaa makes group_rows 0 and the reference divides by zero.
     const uint64_t group_rows64 = 20000ull * (1ull << msaa) / std::max<uint64_t>(w, 1);
     if (group_rows64 == 0) return fail(ctx, EUC_E_UNSUPPORTED, "target width %u > 20000*2^msaa: the reference panics (division by zero, pipeline.rs:330)", w);
     if (w > 65535u || h > 65535u) return fail(ctx, EUC_E_UNSUPPORTED, "target larger than 65535 in a dimension");
     const uint32_t group_rows = (uint32_t)std::min<uint64_t>(group_rows64, 0x7fffffffull);
-    if (h / group_rows == 0) return EUC_OK;  // needed_threads == 0: the reference renders nothing (pipeline.rs:330,337)
+    if (h / group_rows == 0) return plain_clear(true, true);  // needed_threads == 0: the reference renders nothing (pipeline.rs:330,337)
 
     uint32_t row_begin = rc.row_begin, row_end = std::min(rc.row_end, h);
     if (row_begin % TILE) return fail(ctx, EUC_E_INVALID, "row_begin must be a multiple of %d", TILE);
-    if (row_begin >= row_end) return EUC_OK;
+    if (row_begin >= row_end) return plain_clear(true, true);
 
     // draws
     std::vector<DrawDev> dd(rc.n_draws);
@@ -450,7 +500,7 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
         dd[i] = DrawDev{b.first, b.count, b.base_vertex, b.layer, (uint32_t)tri_total, nprim};
         tri_total += nprim;
     }
-    if (tri_total == 0) return EUC_OK;
+    if (tri_total == 0) return plain_clear(true, true);
     if (tri_total > 0x7fffffffull) return fail(ctx, EUC_E_UNSUPPORTED, "too many primitives");
 
     Params prm{};
@@ -461,11 +511,20 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     prm.pixel = pb ? (uint32_t*)pb->d : nullptr;
     prm.depth = db ? (float*)db->d : nullptr;
     prm.depth_test = d.depth_test; prm.depth_write = d.depth_write != 0; prm.pixel_write = pixel_write && !shadow; prm.uses_depth = uses_depth;
-    if (prm.pixel_write && !prm.pixel) return EUC_OK;
+    if (prm.pixel_write && !prm.pixel) return plain_clear(true, true);
     if (uses_depth && !prm.depth) {
         // Empty depth target reads 0.0 and drops writes (texture.rs:312-317); size [0,0] only reaches here when
         // pixel_write is false, which returned above.  With both targets, sizes would have mismatched.
-        return EUC_OK;
+        return plain_clear(true, true);
+    }
+    {   // fused clear: colour when this render writes pixels, depth when it uses the depth target; the rest is filled now
+        const bool fuse_px = clr.px && prm.pixel_write && prm.pixel, fuse_z = clr.z && uses_depth && prm.depth;
+        const euc_ctx::ClearReq req = clr;
+        const int c = plain_clear(!fuse_px, !fuse_z);
+        if (c != EUC_OK) return c;
+        prm.clear_mask = (fuse_px ? 1u : 0u) | (fuse_z ? 2u : 0u);
+        prm.clear_px = req.px_value;
+        std::memcpy(&prm.clear_z, &req.z_value, 4);
     }
     prm.zclip = d.z_clip_enabled != 0; prm.zmin = d.z_clip_min; prm.zmax = d.z_clip_max;
     prm.cull = d.cull_mode; prm.flip_y = d.y_axis_up ? -1.0f : 1.0f;
@@ -718,21 +777,17 @@ int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t ro
     if (!ctx || !texel) return EUC_E_INVALID;
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
-    const Buf& b = it->second;
-    row_end = std::min(row_end, b.h);
-    if (row_begin >= row_end || b.w == 0) return EUC_OK;
     uint32_t v;
     std::memcpy(&v, texel, 4);
-    for (uint32_t l = 0; l < b.layers; ++l) {
-        uint32_t* base = (uint32_t*)b.d + ((size_t)l * b.h + row_begin) * b.w;
-        const size_t n = (size_t)(row_end - row_begin) * b.w;
-        if (((uintptr_t)base & 15u) != 0) return fail(ctx, EUC_E_UNSUPPORTED, "row range is not 16-byte aligned");
-        const size_t vec = (n + 3) / 4;
-        const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
-        ++ctx->launches;
-        fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>(base, n, v);
-    }
-    CU(cudaGetLastError());
+    CU(cudaSetDevice(ctx->dev));
+    return clear_rows_impl(ctx, it->second, v, row_begin, row_end);
+}
+
+int euc_render_clear(euc_ctx* ctx, const void* pixel_texel, const void* depth_texel) {
+    if (!ctx) return EUC_E_INVALID;
+    ctx->next_clear = euc_ctx::ClearReq{};
+    if (pixel_texel) { ctx->next_clear.px = true; std::memcpy(&ctx->next_clear.px_value, pixel_texel, 4); }
+    if (depth_texel) { ctx->next_clear.z = true; std::memcpy(&ctx->next_clear.z_value, depth_texel, 4); }
     return EUC_OK;
 }
 
@@ -875,6 +930,7 @@ int euc_geom_destroy(euc_ctx* ctx, euc_geom geom) {
 
 int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth, uint32_t row_begin,
                          uint32_t row_end) {
+    DropClear drop_clear{ctx};
     if (!ctx || !desc) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
@@ -917,6 +973,7 @@ int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_
 
 int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth, uint32_t row_begin,
                                   uint32_t row_end, const euc_buf* mirrors, uint32_t n_mirrors) {
+    DropClear drop_clear{ctx};
     if (!ctx || !desc || (n_mirrors && !mirrors)) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
@@ -937,11 +994,13 @@ int euc_pipeline_register(euc_ctx* ctx, const char* source, const char* struct_n
 const char* euc_pipeline_log(euc_ctx* ctx) { return (ctx && ctx->user) ? ctx->user->log.c_str() : ""; }
 
 int euc_render_geom(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth) {
+    DropClear drop_clear{ctx};
     return euc_render_geom_rows(ctx, desc, geom, pixel, depth, 0, 0xffffffffu);
 }
 
 int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices,
                const uint32_t* indices, uint32_t n_indices, euc_buf pixel, euc_buf depth) {
+    DropClear drop_clear{ctx};
     if (!ctx || !desc || (!vertices && n_vertices) || vertex_stride == 0) return EUC_E_INVALID;
     CU(cudaSetDevice(ctx->dev));
     int rcode;
@@ -962,8 +1021,8 @@ int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices
 
 int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_batch_draw* draws, uint32_t n_draws,
                      const void* uniforms, euc_buf pixel, euc_buf depth) {
+    DropClear drop_clear{ctx};
     if (!ctx || !desc || (!draws && n_draws)) return EUC_E_INVALID;
-    if (n_draws == 0) return EUC_OK;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
     CU(cudaSetDevice(ctx->dev));

@@ -60,6 +60,11 @@ struct Params {
     uint32_t row_begin, row_end;  // rendered rows (multi-GPU bands); row_begin % 16 == 0
     uint32_t group_rows;          // euc band height (pipeline.rs:329)
     uint32_t msaa_level;
+    // fused clear (euc_render_clear): the render behaves as if its targets' rendered rows had been filled with these values
+    // first; tiles start from the constants instead of loading, and every tile of the rendered rows is written back
+    uint32_t clear_mask;  // bit 0: colour, bit 1: depth
+    uint32_t clear_px;
+    float clear_z;
     uint32_t* pixel;
     float* depth;
     uint32_t* mirrors[EUC_MAX_MIRRORS];  // peer framebuffers that receive this render's colour rows (fused gather)
@@ -1045,24 +1050,46 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     }
     const uint32_t n = rg.y;
     if (n == 0) {
-        // fused gather: a tile without primitives still owes its rows to the mirrors (immediate-mode pipelines; deferred
-        // ones forward from resolve_kernel)
-        if (p.n_mirrors && !DEFER && P::HAS_FRAGMENT && p.pixel_write) {
+        // A tile without primitives still owes its rows to the mirrors (fused gather; immediate-mode pipelines, deferred
+        // ones forward from resolve_kernel) and, under a fused clear, the clear values to its own targets.
+        const bool fwd = p.n_mirrors && !DEFER && P::HAS_FRAGMENT && p.pixel_write;
+        const bool clr_px = (p.clear_mask & 1u) && !DEFER, clr_z = (p.clear_mask & 2u) != 0u;
+        if (fwd || clr_px || clr_z) {
             const uint32_t tpl = p.tiles_x * p.tiles_y, lay = tile / tpl, tl0 = tile - lay * tpl;
             const uint32_t ty0 = tl0 / p.tiles_x, tx0 = tl0 - ty0 * p.tiles_x;
             const uint32_t yy = ty0 * TILE + (lane >> 1), sx = tx0 * TILE + (lane & 1u) * 8u;
             if (yy < p.h && yy >= p.row_begin && yy < p.row_end && sx < p.w) {
                 const size_t bs = (size_t)lay * p.w * p.h + (size_t)yy * p.w + sx;
                 if (sx + 8u <= p.w && (p.w & 3u) == 0) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + bs), b2 = *reinterpret_cast<const uint4*>(p.pixel + bs + 4);
-                    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) {
-                        *reinterpret_cast<uint4*>(p.mirrors[mi] + bs) = a;
-                        *reinterpret_cast<uint4*>(p.mirrors[mi] + bs + 4) = b2;
+                    if (clr_z) {
+                        const float4 z4 = make_float4(p.clear_z, p.clear_z, p.clear_z, p.clear_z);
+                        *reinterpret_cast<float4*>(p.depth + bs) = z4;
+                        *reinterpret_cast<float4*>(p.depth + bs + 4) = z4;
+                    }
+                    if (fwd || clr_px) {
+                        uint4 a, b2;
+                        if (clr_px) {
+                            a = b2 = make_uint4(p.clear_px, p.clear_px, p.clear_px, p.clear_px);
+                            *reinterpret_cast<uint4*>(p.pixel + bs) = a;
+                            *reinterpret_cast<uint4*>(p.pixel + bs + 4) = b2;
+                        } else {
+                            a = *reinterpret_cast<const uint4*>(p.pixel + bs); b2 = *reinterpret_cast<const uint4*>(p.pixel + bs + 4);
+                        }
+                        if (fwd) {
+                            for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) {
+                                *reinterpret_cast<uint4*>(p.mirrors[mi] + bs) = a;
+                                *reinterpret_cast<uint4*>(p.mirrors[mi] + bs + 4) = b2;
+                            }
+                        }
                     }
                 } else {
                     for (uint32_t j = 0; j < 8u && sx + j < p.w; ++j) {
-                        const uint32_t c = p.pixel[bs + j];
-                        for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][bs + j] = c;
+                        if (clr_z) p.depth[bs + j] = p.clear_z;
+                        if (fwd || clr_px) {
+                            uint32_t c;
+                            if (clr_px) { c = p.clear_px; p.pixel[bs + j] = c; } else c = p.pixel[bs + j];
+                            if (fwd) for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][bs + j] = c;
+                        }
                     }
                 }
             }
@@ -1142,7 +1169,10 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     // GREATER; negation is exact and NaN stays NaN, so `sgn*z < sgn*old` has exactly partial_cmp's outcome).
     const bool fast_depth = p.depth_test == EUC_DEPTH_LESS || p.depth_test == EUC_DEPTH_GREATER;
     const float dsgn = p.depth_test == EUC_DEPTH_GREATER ? -1.0f : 1.0f;
-    if (row_ok && p.uses_depth) {
+    if (row_ok && p.uses_depth && (p.clear_mask & 2u)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) depth[j] = p.clear_z;
+    } else if (row_ok && p.uses_depth) {
         if (vec_ok) {
             const float4 a = *reinterpret_cast<const float4*>(p.depth + base), b = *reinterpret_cast<const float4*>(p.depth + base + 4);
             depth[0] = a.x; depth[1] = a.y; depth[2] = a.z; depth[3] = a.w; depth[4] = b.x; depth[5] = b.y; depth[6] = b.z; depth[7] = b.w;
@@ -1156,7 +1186,10 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         for (int j = 0; j < 8; ++j) depth[j] = depth[j] * dsgn;
     }
     if (QUEUE && row_ok && shade_px) {
-        if (vec_ok) {
+        if (p.clear_mask & 1u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cw[j] = p.clear_px;
+        } else if (vec_ok) {
             const uint4 a = *reinterpret_cast<const uint4*>(p.pixel + base), b = *reinterpret_cast<const uint4*>(p.pixel + base + 4);
             cw[0] = a.x; cw[1] = a.y; cw[2] = a.z; cw[3] = a.w; cw[4] = b.x; cw[5] = b.y; cw[6] = b.z; cw[7] = b.w;
         } else {
@@ -1570,7 +1603,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         for (int j = 0; j < 8; ++j) depth[j] = depth[j] * dsgn;
     }
     if (row_ok) {
-        if (p.depth_write) {
+        if (p.depth_write || (p.clear_mask & 2u)) {
             if (vec_ok) {
                 *reinterpret_cast<float4*>(p.depth + base) = make_float4(depth[0], depth[1], depth[2], depth[3]);
                 *reinterpret_cast<float4*>(p.depth + base + 4) = make_float4(depth[4], depth[5], depth[6], depth[7]);
@@ -1674,7 +1707,10 @@ template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128)
             const size_t idx = (size_t)layer * p.w * p.h + (size_t)y * p.w + x;
             const uint32_t win = p.winner[idx];
             if (win == NO_WINNER) {
-                if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
+                if (p.clear_mask & 1u) {  // fused clear: untouched pixels take the clear value
+                    p.pixel[idx] = p.clear_px;
+                    for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = p.clear_px;
+                } else if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
                     const uint32_t c = p.pixel[idx];
                     for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
                 }
@@ -1707,12 +1743,14 @@ template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128)
             const uint32_t ya = max(band_lo + (kc << Lv), p.row_begin), yb = min(min(band_lo + ((kc + 1u) << Lv), band_hi), row_end);
             const uint32_t xa = cxi << Lv, xb = min(xa + cs, p.w);
             const size_t lay = (size_t)layer * p.w * p.h;
-            if (p.n_mirrors) {  // fused gather: untouched pixels of this rank's rows are forwarded as they are
+            if (p.n_mirrors || (p.clear_mask & 1u)) {
+                // untouched pixels: the clear value under a fused clear; forwarded to the mirrors under the fused gather
                 for (uint32_t y = ya; y < yb; ++y)
                     for (uint32_t x = xa; x < xb; ++x) {
                         const size_t idx = lay + (size_t)y * p.w + x;
                         if (p.winner[idx] == NO_WINNER) {
-                            const uint32_t c = p.pixel[idx];
+                            uint32_t c;
+                            if (p.clear_mask & 1u) { c = p.clear_px; p.pixel[idx] = c; } else c = p.pixel[idx];
                             for (uint32_t mi = 0; mi < p.n_mirrors; ++mi) p.mirrors[mi][idx] = c;
                         }
                     }

@@ -201,6 +201,14 @@ int euc_buf_destroy(euc_ctx* ctx, euc_buf buf);
 int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel);                     /* all layers */
 /* Clear rows [row_begin, row_end) of every layer only (row-band rendering: the other rows belong to other ranks). */
 int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t row_begin, uint32_t row_end);
+/* Fused clear: the NEXT render call of this context behaves as if its pixel target had first been cleared to *pixel_texel
+ * and its depth target to *depth_texel (rows it renders, every layer; NULL = leave that target alone) -- the sequence
+ * `color.clear(..); depth.clear(..); pipe.render(..)` of benches/teapot.rs:183-204 in one call.  The tile kernels start
+ * from the constants instead of loading the targets and write every tile of the rendered rows, which saves one full
+ * write and one full read of both targets per frame.  A target the render does not use (pixel target of a depth-only
+ * pass, depth target under DepthMode::NONE) is filled the ordinary way before the render.  The request is consumed by the
+ * next euc_render* call, also when that call draws nothing; it is dropped if that call fails validation. */
+int euc_render_clear(euc_ctx* ctx, const void* pixel_texel, const void* depth_texel);
 int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes);       /* row-major, x + w*y, layer-major */
 int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes);           /* blocking */
 /* Row N4 (host I/O around the path): pinned host memory and asynchronous read-back, so that a consumer in the style of

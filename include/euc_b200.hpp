@@ -30,6 +30,8 @@ public:
     euc_ctx* raw() const { return ctx_; }
     void check(int rc) const { if (rc != EUC_OK) throw Error(rc, euc_last_error(ctx_)); }
     void sync() const { check(euc_sync(ctx_)); }
+    // `pixel.clear(a); depth.clear(b); pipe.render(..)` with the clears fused into the next render (null = leave alone)
+    void render_clear(const uint32_t* pixel_value, const float* depth_value) const { check(euc_render_clear(ctx_, pixel_value, depth_value)); }
 private:
     euc_ctx* ctx_ = nullptr;
 };
