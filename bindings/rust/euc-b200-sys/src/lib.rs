@@ -70,6 +70,8 @@ extern "C" {
     pub fn euc_buf_destroy(ctx: *mut euc_ctx, buf: euc_buf) -> c_int;
     pub fn euc_buf_clear(ctx: *mut euc_ctx, buf: euc_buf, texel: *const c_void) -> c_int;
     pub fn euc_buf_clear_rows(ctx: *mut euc_ctx, buf: euc_buf, texel: *const c_void, row_begin: u32, row_end: u32) -> c_int;
+    /// The next render first clears its targets (null = leave alone), fused into its kernels.
+    pub fn euc_render_clear(ctx: *mut euc_ctx, pixel_texel: *const c_void, depth_texel: *const c_void) -> c_int;
     pub fn euc_buf_upload(ctx: *mut euc_ctx, buf: euc_buf, host: *const c_void, bytes: usize) -> c_int;
     pub fn euc_buf_download(ctx: *mut euc_ctx, buf: euc_buf, host: *mut c_void, bytes: usize) -> c_int;
     pub fn euc_geom_create(ctx: *mut euc_ctx, vertices: *const c_void, stride: u32, n_vertices: u32,
