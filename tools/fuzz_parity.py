@@ -66,4 +66,56 @@ while time.time() < t_end:
     dmax = np.abs(gpx.view(np.uint8).astype(np.int16) - rpx.view(np.uint8).astype(np.int16)).max()
     assert dmax <= 1, what + f" colour differs by {dmax}"
     n_scenes += 1; n_frag += rs["fragments"]
-print(f"fuzz ok: {n_scenes} scenes, {n_frag} fragments, seed {seed0}, {budget:.0f} s")
+print(f"fuzz ok: {n_scenes} triangle scenes, {n_frag} fragments, seed {seed0}, {budget:.0f} s")
+
+# ---- samplers (textured cube, random texture / filter / wrap / uv scale / pose) and lines -------------------------------
+t_end = time.time() + budget / 3
+n_cube = n_lines = 0
+while time.time() < t_end:
+    k += 1
+    rng = np.random.default_rng(seed0 * 100003 + k)
+    w = int(rng.choice([320, 640, 1000, 1920])); h = int(rng.choice([200, 480, 1080]))
+    if rng.random() < 0.6:
+        th, tw = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        tex = rng.integers(0, 256, size=(th, tw, 4), dtype=np.uint8)
+        verts, idx = scenes.cube_geometry(uv_scale=float(rng.choice([1.0, 3.0, -2.5, 0.37, 17.0])))
+        mvp = scenes.cube_mvp(int(rng.integers(0, 2000)), w, h)
+        filt, wrap = str(rng.choice(["linear", "nearest"])), str(rng.choice(["tiled", "mirrored", "clamped", "none"]))
+
+        def make(t):
+            if isinstance(t, e.Buffer2d):
+                sm = t.linear() if filt == "linear" else t.nearest()
+            else:
+                sm = e.Sampler(t.view(np.uint32).reshape(t.shape[0], t.shape[1]), e.abi.TEXEL_RGBA8_TO_F32,
+                               e.abi.FILTER_LINEAR if filt == "linear" else e.abi.FILTER_NEAREST)
+            return e.Cube(mvp, {"tiled": sm.tiled, "mirrored": sm.mirrored, "clamped": sm.clamped, "none": lambda: sm}[wrap]())
+        px = e.Buffer2d.fill([w, h], 0, dtype=np.uint32)
+        make(e.Buffer2d.from_array(tex)).render(e.IndexedVertices(idx, verts), px, e.Empty(), clear=(180, None))
+        gfr = ctx.get_stats()["fragments"]
+        rpx = np.full((h, w), 180, np.uint32)
+        rs = oracle.render(make(tex), e.IndexedVertices(idx, verts), rpx, None, n_threads=0)
+        what = f"cube scene {k} seed {seed0}: {w}x{h} tex {tw}x{th} {filt} {wrap}"
+        n_cube += 1
+    else:
+        n = int(rng.choice([2, 20, 400]))
+        v = np.zeros(2 * n, dtype=e.VERTEX_P4C4)
+        wv = np.where(rng.random(2 * n) < 0.5, 1.0, 0.2 + 2.0 * rng.random(2 * n)).astype(np.float32)
+        v["pos"][:, 0] = (rng.random(2 * n) * 3 - 1.5) * wv; v["pos"][:, 1] = (rng.random(2 * n) * 3 - 1.5) * wv
+        v["pos"][:, 2] = (rng.random(2 * n) * 1.2 - 0.1) * wv; v["pos"][:, 3] = wv
+        v["rgba"] = rng.random((2 * n, 4), dtype=np.float32)
+        depth = [e.DepthMode.LESS_WRITE, e.DepthMode.NONE][int(rng.integers(0, 2))]
+        pipe = lambda: e.VertexColor(primitives=e.LineList, depth=depth)
+        px = e.Buffer2d.fill([w, h], 0, dtype=np.uint32)
+        z = e.Buffer2d.fill([w, h], 1.0) if depth.uses_depth() else e.Empty()
+        pipe().render(v, px, z)
+        gfr = ctx.get_stats()["fragments"]
+        rpx = np.zeros((h, w), np.uint32); rz = np.full((h, w), 1.0, np.float32) if depth.uses_depth() else None
+        rs = oracle.render(pipe(), v, rpx, rz, n_threads=0)
+        what = f"line scene {k} seed {seed0}: {w}x{h} n={n} {depth}"
+        if rz is not None:
+            assert np.array_equal(z.raw().view(np.uint32), rz.view(np.uint32)), what + " depth differs"
+        n_lines += 1
+    assert gfr == rs["fragments"], what + f" fragments {gfr} != {rs['fragments']}"
+    dmax = np.abs(px.raw().view(np.uint8).astype(np.int16) - rpx.view(np.uint8).astype(np.int16)).max()
+    assert dmax <= 1, what + f" colour differs by {dmax}"
+print(f"fuzz ok: {n_cube} textured-cube scenes, {n_lines} line scenes")
