@@ -23,6 +23,13 @@ impl Context {
         Err(Error { code: rc, message })
     }
     pub fn sync(&self) -> Result<(), Error> { self.check(unsafe { sys::euc_sync(self.raw) }) }
+    /// `color.clear(a); depth.clear(b);` of benches/teapot.rs:183-185 attached to the next `render`: the clears are fused into
+    /// its kernels (`None` leaves that target alone).
+    pub fn render_clear(&self, pixel: Option<u32>, depth: Option<f32>) -> Result<(), Error> {
+        let p = pixel.as_ref().map_or(std::ptr::null(), |v| v as *const u32 as *const _);
+        let d = depth.as_ref().map_or(std::ptr::null(), |v| v as *const f32 as *const _);
+        self.check(unsafe { sys::euc_render_clear(self.raw, p, d) })
+    }
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::euc_shutdown(self.raw); } } }
 
