@@ -434,14 +434,32 @@ def run_ours(args, rank, world, local_rank):
         def frame():
             pipe.render_batch(geom, scene["draws"], scene["ubs"], color, depth, clear=(0, 1.0))
 
-        def frame_e2e():
-            geom.update(pv.data_ptr(), pi.data_ptr())
-            frame()
-            ctx._check(ctx._lib.euc_buf_download(ctx._p, color.handle, host_out.data_ptr(), n * h * w * 4))
+        def make_icon_slot(cx, st, geom_s, color_s, depth_s):
+            """One in-flight batch of the e2e loop: upload of the geometry, render, asynchronous read-back of all icons."""
+            with torch.cuda.stream(st):
+                out_s = torch.empty(n * h * w, dtype=torch.int32).pin_memory()
+            dev = color_s.as_torch()
+            keep.extend([out_s, dev, geom_s, color_s, depth_s])
+
+            def fe2e():
+                geom_s.update(pv.data_ptr(), pi.data_ptr())
+                pipe.render_batch(geom_s, scene["draws"], scene["ubs"], color_s, depth_s, clear=(0, 1.0))
+                out_s.copy_(dev[: n * h * w], non_blocking=True)
+            return fe2e
+
+        frame_e2e = make_icon_slot(ctx, stream, geom, color, depth)
+        stream2 = torch.cuda.Stream()
+        ctx2 = e.Context(local_rank)
+        ctx2.set_stream(stream2.cuda_stream)
+        frame_e2e_b = make_icon_slot(ctx2, stream2, e.Geometry(scene["verts"], scene["idx"], ctx2), e.Buffer2d([w, h], np.uint32, ctx2, layers=n),
+                                     e.Buffer2d([w, h], np.float32, ctx2, layers=n))
+        keep += [ctx2, stream2]
+        pipelined = ([frame_e2e, frame_e2e_b], [stream, stream2])
 
         h2d, d2h = pv.numel() + pi.numel(), n * h * w * 4
         config_extra = {"partition": f"{n} icons per rank x {world} rank(s), no collective", "icons_per_step": n * world,
-                        "l2": f"targets {n * w * h * 8 / 1e6:.0f} MB > 126 MB L2; no flush"}
+                        "l2": f"targets {n * w * h * 8 / 1e6:.0f} MB > 126 MB L2; no flush",
+                        "e2e_pipeline": "2 batches in flight (2 contexts / streams): H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i"}
 
     flush_buf = torch.empty(64 * 1024 * 1024, dtype=torch.int32, device="cuda") if wl in ("c1", "c2") else None
 
