@@ -1,11 +1,13 @@
 """ctypes mirror of include/euc_b200.h (POD structs and enums only — no library loading here)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SAMPLERS = 2
 PIPE_USER_BASE = 1000
 IPC_HANDLE_BYTES = 64
 MAX_MIRRORS = 7
+MAX_GROUP = 8
+GATHER_NONE, GATHER_ROOT, GATHER_ALL = range(3)
 
 # enum euc_status
 OK, E_INVALID, E_SIZE_MISMATCH, E_UNSUPPORTED, E_CUDA, E_OOM, E_OUT_OF_BOUNDS = 0, -1, -2, -3, -4, -5, -6
@@ -58,6 +60,8 @@ SYMBOLS = {
     "euc_last_error": (C.c_char_p, [_ctx_p]),
     "euc_set_stream": (C.c_int, [_ctx_p, C.c_void_p]),
     "euc_sync": (C.c_int, [_ctx_p]),
+    "euc_set_async": (C.c_int, [_ctx_p, C.c_int]),
+    "euc_blocking_waits": (C.c_uint64, [_ctx_p]),
     "euc_set_stats": (C.c_int, [_ctx_p, C.c_int]),
     "euc_get_stats": (C.c_int, [_ctx_p, C.POINTER(RenderStats)]),
     "euc_buf_create": (C.c_int, [_ctx_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
@@ -71,6 +75,7 @@ SYMBOLS = {
     "euc_host_free": (C.c_int, [_ctx_p, C.c_void_p]),
     "euc_buf_download_async": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "euc_ticket_wait": (C.c_int, [_ctx_p, C.c_uint64]),
+    "euc_buf_download_rows_async": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_buf_device_ptr": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "euc_buf_size": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "euc_buf_wrap": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
@@ -80,6 +85,7 @@ SYMBOLS = {
     "euc_geom_create": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_geom_wrap": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_geom_update": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "euc_geom_update_range": (C.c_int, [_ctx_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]),
     "euc_geom_destroy": (C.c_int, [_ctx_p, C.c_uint64]),
     "euc_render": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
     "euc_render_geom": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64]),
@@ -88,6 +94,14 @@ SYMBOLS = {
     "euc_buf_ipc_import": (C.c_int, [_ctx_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "euc_render_geom_rows_mirrored": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                                 C.POINTER(C.c_uint64), C.c_uint32]),
+    "euc_group_create": (C.c_int, [_ctx_p, C.c_char_p, C.c_uint32, C.c_uint32]),
+    "euc_group_destroy": (C.c_int, [_ctx_p]),
+    "euc_group_share_buf": (C.c_int, [_ctx_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "euc_group_barrier": (C.c_int, [_ctx_p]),
+    "euc_group_rows": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "euc_group_frames": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "euc_group_allgather_geom": (C.c_int, [_ctx_p, C.c_uint64]),
+    "euc_group_render": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.c_int]),
     "euc_pipeline_register": (C.c_int, [_ctx_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]),
     "euc_pipeline_log": (C.c_char_p, [_ctx_p]),
     "euc_render_batch": (C.c_int, [_ctx_p, C.POINTER(PipelineDesc), C.c_uint64, C.POINTER(BatchDraw), C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]),

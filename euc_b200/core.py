@@ -137,6 +137,25 @@ class Context:
         zv = C.c_float(float(depth_value)) if depth_value is not None else None
         self._check(self._lib.euc_render_clear(self._p, C.byref(pv) if pv is not None else None, C.byref(zv) if zv is not None else None))
 
+    def ticket_wait(self, ticket):
+        self._check(self._lib.euc_ticket_wait(self._p, int(ticket)))
+
+    def host_alloc(self, nbytes):
+        """Pinned host memory (euc_host_alloc); returns its address.  Freed with host_free."""
+        p = C.c_void_p()
+        self._check(self._lib.euc_host_alloc(self._p, int(nbytes), C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr):
+        self._check(self._lib.euc_host_free(self._p, C.c_void_p(ptr)))
+
+    def set_async(self, enabled):
+        """euc_set_async: renders never wait for the device (default on); False = every render call is checked."""
+        self._check(self._lib.euc_set_async(self._p, 1 if enabled else 0))
+
+    def blocking_waits(self):
+        return int(self._lib.euc_blocking_waits(self._p))
+
     def set_stats(self, enabled):
         self._check(self._lib.euc_set_stats(self._p, 1 if enabled else 0))
 
@@ -290,6 +309,16 @@ class Buffer2d:
         self.ctx._check(self.ctx._lib.euc_buf_download(self.ctx._p, self.handle, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def download_async(self, host_ptr, rows=None):
+        """Asynchronous read-back into (pinned) host memory at `host_ptr`: the whole buffer, or rows (r0, r1) of a single-layer
+        buffer, tightly packed.  Returns a ticket for Context.ticket_wait."""
+        t = C.c_uint64()
+        if rows is None:
+            self.ctx._check(self.ctx._lib.euc_buf_download_async(self.ctx._p, self.handle, C.c_void_p(host_ptr), self._size[0] * self._size[1] * self.layers * 4, C.byref(t)))
+        else:
+            self.ctx._check(self.ctx._lib.euc_buf_download_rows_async(self.ctx._p, self.handle, C.c_void_p(host_ptr), int(rows[0]), int(rows[1]), C.byref(t)))
+        return t.value
+
     def ipc_export(self) -> bytes:
         """CUDA IPC handle of this buffer (for another process on the same node)."""
         h = C.create_string_buffer(abi.IPC_HANDLE_BYTES)
@@ -374,6 +403,12 @@ class Geometry:
         """Re-upload from host memory (raw addresses, e.g. of pinned buffers); asynchronous on the context's stream."""
         self.ctx._check(self.ctx._lib.euc_geom_update(self.ctx._p, self.handle, C.c_void_p(vertices_ptr),
                                                       C.c_void_p(indices_ptr) if indices_ptr else None))
+
+    def update_range(self, vertices_ptr, first_vertex, n_vertices, indices_ptr=None, first_index=0, n_indices=0):
+        """Re-upload a slice (raw host addresses of the slice's first vertex / index); asynchronous when pinned."""
+        self.ctx._check(self.ctx._lib.euc_geom_update_range(self.ctx._p, self.handle, C.c_void_p(vertices_ptr) if vertices_ptr else None,
+                                                            int(first_vertex), int(n_vertices), C.c_void_p(indices_ptr) if indices_ptr else None,
+                                                            int(first_index), int(n_indices)))
 
     def destroy(self):
         if self.handle:
@@ -462,7 +497,9 @@ class Pipeline:
         ctx = ctx or default_context()
         d, keep = getattr(self, "_frozen", None) or self.build_desc(lambda s: s.texture.handle)
         lib = ctx._lib
-        if clear is not None:
+        if rows is not None and not isinstance(vertices, Geometry):
+            raise ValueError("row-restricted rendering needs a device-resident Geometry")
+        if clear is not None:  # armed only once the arguments are known to be good: the request belongs to THIS render
             ctx.render_clear(*clear)
         if isinstance(vertices, Geometry):
             if mirrors:
@@ -474,8 +511,6 @@ class Pipeline:
             else:
                 rc = lib.euc_render_geom_rows(ctx._p, C.byref(d), vertices.handle, pixel.handle, depth.handle, rows[0], rows[1])
         else:
-            if rows is not None:
-                raise ValueError("row-restricted rendering needs a device-resident Geometry")
             if isinstance(vertices, IndexedVertices):
                 v, idx = np.ascontiguousarray(vertices.verts), vertices.indices
             else:

@@ -32,7 +32,19 @@ struct Geom {
     uint32_t* idx = nullptr;
     uint32_t n_idx = 0;
     bool owned = true;
+    // smallest / largest index, when the library has seen the indices on the host (euc_geom_create, small euc_render
+    // streams): a render whose draws are in range by these bounds cannot fail with EUC_E_OUT_OF_BOUNDS and therefore has
+    // nothing to wait for.  Unknown bounds: the device checks, and the error is deferred (see euc_set_async).
+    bool bounds_known = false;
+    uint32_t idx_min = 0, idx_max = 0;
 };
+// Index bounds of a host index array (one pass; auto-vectorised)
+void index_bounds(const uint32_t* idx, size_t n, uint32_t& lo, uint32_t& hi) {
+    uint32_t a = 0xffffffffu, b = 0u;
+    for (size_t i = 0; i < n; ++i) { a = idx[i] < a ? idx[i] : a; b = idx[i] > b ? idx[i] : b; }
+    lo = n ? a : 0u; hi = b;
+}
+constexpr size_t HOST_SCAN_MAX_INDICES = 1u << 16;  // euc_render / euc_geom_update scan host indices up to this many per call
 struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
@@ -40,8 +52,12 @@ struct Scratch {
 
 }  // namespace
 
+namespace { struct PipeOps; }
 struct euc_user_pipes;
+struct euc_group;
 struct euc_ctx {
+    euc_group* group = nullptr;  // multi-GPU group this context belongs to (group.inc)
+    std::unordered_map<int, PipeOps*> builtin;  // kernel launchers of the built-in pipelines used so far (key: pipeline id * 2 + lines)
     euc_user_pipes* user = nullptr;  // pipelines compiled at run time (runtime_pipeline.inc)
     int dev = 0;
     cudaStream_t own = nullptr, stream = nullptr;
@@ -49,9 +65,22 @@ struct euc_ctx {
     uint64_t next_handle = 1;
     std::unordered_map<uint64_t, Buf> bufs;
     std::unordered_map<uint64_t, Geom> geoms;
-    Scratch recs, bbox, tile_count, tile_range, tile_list, draws, uniforms, tmp_verts, tmp_idx, winner;
-    unsigned long long* counters = nullptr;      // device, 8 words: pairs, fragments, list cursor, flags, tile ticket
+    Scratch recs, bbox, tile_count, tile_range, tile_list, draws, uniforms, tmp_verts, tmp_idx, winner, ovf, ext;
+    unsigned long long* counters = nullptr;      // device, CTR_WORDS words (kernels.cuh: Params::counters); word 15 = sticky flags
     unsigned long long* counters_host = nullptr;  // pinned
+    // Asynchronous renders (euc_set_async, default on): no host wait inside a render call.  The last raster warp of a render
+    // publishes its summary into `summary` (mapped pinned memory); the host reads it at the start of later calls.
+    bool async = true;
+    volatile unsigned long long* summary = nullptr;      // host view
+    unsigned long long* summary_dev = nullptr;           // device view of the same memory
+    unsigned long long seq = 0, seen_seq = 0;
+    uint64_t ovf_want = 0;                                // overflow-buffer entries wanted by past renders
+    int deferred_code = EUC_OK;                           // error of an earlier asynchronous render, reported by the next call
+    std::string deferred_msg;
+    int launch_err = 0;                                   // first failed driver-API launch of a run-time pipeline (CUresult)
+    uint64_t blocking_waits = 0;                          // host waits inside render calls (diagnostics: 0 in steady state)
+    void* stage_host[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; cudaEvent_t stage_ev[2] = {nullptr, nullptr};  // pinned staging of batch tables
+    bool stage_used[2] = {false, false}; int stage_next = 0;
     bool stats = false;
     struct ClearReq { bool px = false, z = false; uint32_t px_value = 0, z_value = 0; } next_clear;  // euc_render_clear: consumed by the next render
     int sparse_recs = -1;  // EUC_SPARSE_RECS (development): -1 = automatic, 0 / 1 = force
@@ -64,7 +93,8 @@ struct euc_ctx {
     bool profiling = false;
     cudaEvent_t ev_counts = nullptr, ev_setup = nullptr;
     cudaStream_t aux = nullptr;  // counter read-back
-    std::unordered_map<uint32_t, uint32_t> bin_cap_hint;  // per tile-count: bin size of the fast path (0 = use the exact path)
+    struct BinHint { uint32_t cap = 128; bool verified = false; };  // cap 0 = use the exact path
+    std::unordered_map<uint32_t, BinHint> bin_hint;       // per tile-count: bin size of the fast path
     std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[EUC_STAGE_COUNT] = {};
@@ -90,8 +120,48 @@ int fail(euc_ctx* c, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? EUC_E_OOM : EUC_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int CTR_WORDS = 16;        // device counters of a context (kernels.cuh: Params::counters)
+constexpr int CTR_CLEAR_WORDS = 12;  // zeroed per render; word 15 keeps the sticky flags until the host has seen them
+
+// Reads the summary of the most recent finished asynchronous render (mapped pinned memory, no CUDA call): grows the bin /
+// overflow sizes for later renders and latches device-detected errors, which the next API call reports.
+void poll_summary(euc_ctx* ctx) {
+    if (!ctx->summary) return;
+    if (ctx->summary[6]) {  // a group barrier gave up waiting for a peer
+        ctx->summary[6] = 0;
+        if (ctx->deferred_code == EUC_OK) { ctx->deferred_code = EUC_E_CUDA; ctx->deferred_msg = "a group barrier timed out: a peer rank never arrived"; }
+    }
+    const unsigned long long s0 = ctx->summary[0];
+    if (s0 == ctx->seen_seq) return;
+    const unsigned long long flags = ctx->summary[1], longest = ctx->summary[2], ovf = ctx->summary[3], tiles = ctx->summary[5];
+    if (ctx->summary[0] != s0) return;  // a newer render is publishing right now: look again at the next call
+    ctx->seen_seq = s0;
+    auto it = ctx->bin_hint.find((uint32_t)tiles);
+    if (it != ctx->bin_hint.end() && it->second.cap) {
+        const unsigned long long want = ((longest + longest / 4 + 32) + 31) / 32 * 32;
+        if (want > it->second.cap) it->second.cap = (want * tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
+    }
+    if (ovf * 2 > ctx->ovf_want) ctx->ovf_want = ovf * 2;
+    if ((flags & 5ull) && ctx->deferred_code == EUC_OK) {
+        if (flags & 1ull) { ctx->deferred_code = EUC_E_OUT_OF_BOUNDS; ctx->deferred_msg = "vertex index out of range in an earlier asynchronous render (that render drew nothing)"; }
+        else { ctx->deferred_code = EUC_E_OOM; ctx->deferred_msg = "an earlier asynchronous render overflowed its bin-overflow buffer and drew nothing; the buffer has been enlarged, re-issue the frame"; }
+        cudaMemsetAsync(ctx->counters + 15, 0, sizeof(unsigned long long), ctx->stream);
+    }
+}
+
+struct DeviceGuard {  // every entry point works on its context's device, whatever device the calling thread had current
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(euc_ctx* ctx) { if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->dev) switched = cudaSetDevice(ctx->dev) == cudaSuccess; }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 int ensure(euc_ctx* ctx, Scratch& s, size_t bytes, bool zero_new = false) {
     if (bytes <= s.cap) return EUC_OK;
+    {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(ctx->stream, &st);
+        if (st != cudaStreamCaptureStatusNone) return fail(ctx, EUC_E_UNSUPPORTED, "a scratch buffer must grow: run this render once outside stream capture");
+    }
     size_t cap = bytes + bytes / 4 + 4096;
     if (s.p) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -154,6 +224,7 @@ struct RenderCall {
     uint32_t row_begin, row_end;
     const euc_buf* mirrors = nullptr;
     uint32_t n_mirrors = 0;
+    bool maybe_oob_sync = false;  // the host knows the index bounds and they do not prove every draw in range: checked render
 };
 
 // What the render driver needs from a pipeline: sizes, flags, and how to launch its kernels on ctx->stream.
@@ -165,6 +236,7 @@ struct PipeOps {
     std::function<void(const Params&, bool msaa, uint32_t blocks, uint32_t n_tiles)> raster;
     std::function<void(const Params&, bool msaa, uint32_t grid)> resolve;
     std::function<int(bool msaa)> resident;
+    int resident_cache[2] = {0, 0};  // per context (the smem attribute must be set on every device)
 };
 
 // Fills rows [row_begin, row_end) of every layer of a buffer (Target::clear restricted to a row range).
@@ -183,7 +255,6 @@ static int clear_rows_impl(euc_ctx* ctx, const Buf& b, uint32_t v, uint32_t row_
     for (uint32_t l = 0; l < b.layers; ++l) {
         uint32_t* base = (uint32_t*)b.d + ((size_t)l * b.h + row_begin) * b.w;
         const size_t n = (size_t)(row_end - row_begin) * b.w;
-        if (((uintptr_t)base & 15u) != 0) return fail(ctx, EUC_E_UNSUPPORTED, "row range is not 16-byte aligned");
         const size_t vec = (n + 3) / 4;
         const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
         ++ctx->launches;
@@ -282,26 +353,63 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
         CU(cudaEventRecord(ctx->ev_counts, ctx->aux));
         return EUC_OK;
     };
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &cap_st);
+    const bool capturing = cap_st != cudaStreamCaptureStatusNone;
 
     // ---- fast path: fixed-capacity bins.  setup appends primitive ids straight into tile*cap + slot; raster follows.
-    // The capacity is a per-context hint (longest list seen, with headroom).  A tile that overflows flags the render;
-    // raster then exits at once and the whole render is redone on the exact path below.
-    uint32_t cap = 128;
+    // The capacity is a per-context hint (longest list seen, with headroom).
+    //   * asynchronous (steady state): a pair that does not fit its bin goes to the overflow buffer and the raster warp of
+    //     that tile collects it from there, so the result is right whatever the hint was and the host waits for nothing.
+    //     The render's summary (longest list, overflow volume, flags) reaches the host through mapped pinned memory and
+    //     sizes later renders.
+    //   * checked (first render of a target shape, renders that could read a vertex out of range, euc_set_async(0)): the
+    //     host waits for setup's flags; an overflowing bin makes raster exit at once and the render is redone on the exact
+    //     path below, which also measures the longest list.
+    euc_ctx::BinHint hint;
     {
-        auto it = ctx->bin_cap_hint.find(n_tiles);
-        if (it != ctx->bin_cap_hint.end()) cap = it->second;
+        auto it = ctx->bin_hint.find(n_tiles);
+        if (it != ctx->bin_hint.end()) hint = it->second;
     }
+    const uint32_t cap = hint.cap;
     const bool fast = cap > 0 && (size_t)n_tiles * cap * 4 <= ((size_t)1 << 30);
+    const bool go_async = fast && ctx->async && hint.verified && !rc.maybe_oob_sync;
+    if (capturing && !go_async)
+        return fail(ctx, EUC_E_UNSUPPORTED, "this render needs a host check (first render of a target shape, or index bounds the host cannot prove): run it once outside stream capture");
     if (fast) {
         if ((rcode = ensure(ctx, ctx->tile_list, (size_t)n_tiles * cap * 4)) != EUC_OK) return rcode;
         prm.tile_list = (uint32_t*)ctx->tile_list.p;
         prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
         prm.bin_cap = cap;
-        CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        if (ctx->async) {
+            // sized on the checked render already: the asynchronous renders that follow (possibly inside stream capture) find them
+            const uint64_t want = std::max<uint64_t>({(uint64_t)1 << 18, (uint64_t)prm.n_tris * 2, ctx->ovf_want});
+            if ((rcode = ensure(ctx, ctx->ovf, (size_t)want * sizeof(uint2))) != EUC_OK) return rcode;
+            if ((rcode = ensure(ctx, ctx->ext, (size_t)want * 4)) != EUC_OK) return rcode;
+        }
+        if (go_async) {
+            prm.ovf = (uint2*)ctx->ovf.p;
+            prm.ext = (uint32_t*)ctx->ext.p;
+            prm.ovf_cap = (uint32_t)std::min<uint64_t>(std::min(ctx->ovf.cap / sizeof(uint2), ctx->ext.cap / 4), 0x7fffffffull);
+            prm.summary = ctx->summary_dev;
+            prm.seq = ++ctx->seq;
+        }
+        CU(cudaMemsetAsync(ctx->counters, 0, CTR_CLEAR_WORDS * sizeof(unsigned long long), ctx->stream));
         { StageTimer t(ctx, EUC_STAGE_SETUP); ops.setup(prm, tri_blocks); }
+        if (go_async) {
+            launch_raster();
+            CU(cudaGetLastError());
+            if (ctx->launch_err) { const int le = ctx->launch_err; ctx->launch_err = 0; return fail(ctx, EUC_E_CUDA, "kernel launch of a run-time pipeline failed (CUresult %d)", le); }
+            ctx->last.primitives = prm.n_tris;
+            ctx->last.binned_pairs = 0;  // on the device; euc_get_stats reads it
+            ctx->last.fragments = 0;
+            return EUC_OK;
+        }
         if ((rcode = fetch_counters()) != EUC_OK) return rcode;
         launch_raster();
         CU(cudaGetLastError());
+        if (ctx->launch_err) { const int le = ctx->launch_err; ctx->launch_err = 0; return fail(ctx, EUC_E_CUDA, "kernel launch of a run-time pipeline failed (CUresult %d)", le); }
+        ++ctx->blocking_waits;
         CU(cudaEventSynchronize(ctx->ev_counts));  // waits for setup only; raster is already queued behind it
         ctx->last.primitives = prm.n_tris;
         ctx->last.binned_pairs = ctx->counters_host[0];
@@ -310,22 +418,27 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
             CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
             return fail(ctx, EUC_E_OUT_OF_BOUNDS, "vertex index out of range");
         }
-        if (!(ctx->counters_host[3] & 2ull)) return EUC_OK;
+        if (!(ctx->counters_host[3] & 2ull)) {
+            hint.verified = true;  // this shape fits bins of `cap`: later renders run asynchronously
+            ctx->bin_hint[n_tiles] = hint;
+            return EUC_OK;
+        }
         // overflow: raster skipped itself.  Reset the tile counters and fall through to the exact path, which also
         // measures the longest list for the next render's capacity.
         CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, ctx->stream));
-        ctx->bin_cap_hint[n_tiles] = 0;
     }
 
     // ---- exact path: count (setup) -> alloc -> fill -> raster.  The pair list is sized optimistically (grow-only) so
     // that fill and raster can be queued before the host knows the pair count: the GPU never waits for the host.
     // alloc_tiles flags a list that is too small, fill/raster then exit immediately, and the host re-launches them.
     prm.bin_cap = 0;
+    prm.ovf_cap = 0;
+    prm.summary = nullptr;
     if ((rcode = ensure(ctx, ctx->tile_list, std::max<size_t>((size_t)prm.n_tris * 3, 1u << 16) * 4)) != EUC_OK) return rcode;
     prm.tile_list = (uint32_t*)ctx->tile_list.p;
     prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
 
-    CU(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->counters, 0, CTR_CLEAR_WORDS * sizeof(unsigned long long), ctx->stream));
     auto launch_fill_raster = [&]() {
         { StageTimer t(ctx, EUC_STAGE_FILL); fill_kernel<<<tri_blocks, 128, 0, ctx->stream>>>(prm); }
         launch_raster();
@@ -339,6 +452,8 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     CU(cudaMemsetAsync(ctx->counters + 1, 0, sizeof(unsigned long long), ctx->stream));
     launch_fill_raster();
     CU(cudaGetLastError());
+    if (ctx->launch_err) { const int le = ctx->launch_err; ctx->launch_err = 0; return fail(ctx, EUC_E_CUDA, "kernel launch of a run-time pipeline failed (CUresult %d)", le); }
+    ++ctx->blocking_waits;
     CU(cudaEventSynchronize(ctx->ev_counts));  // waits for setup + alloc only; fill and raster are already queued behind
     const unsigned long long pairs = ctx->counters_host[0];
     ctx->last.primitives = prm.n_tris;
@@ -352,7 +467,9 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     {   // capacity hint for the fast path of the next render with this tile configuration
         const unsigned long long longest = ctx->counters_host[1];
         const unsigned long long want = ((longest + longest / 4 + 32) + 31) / 32 * 32;
-        ctx->bin_cap_hint[n_tiles] = (want * n_tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
+        hint.cap = (want * n_tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
+        hint.verified = hint.cap != 0;
+        ctx->bin_hint[n_tiles] = hint;
     }
     if (ctx->counters_host[3] & 2ull) {
         if (pairs > 0xfffffff0ull) {
@@ -369,11 +486,13 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     return EUC_OK;
 }
 
-// PipeOps of a built-in pipeline: template instantiations of the kernels.
-template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx) {
-    static thread_local PipeOps ops;
-    static thread_local euc_ctx* bound = nullptr;
-    if (bound == ctx) return ops;
+// PipeOps of a built-in pipeline: template instantiations of the kernels.  One set per context and pipeline (the shared
+// memory attribute of the raster kernel is per device, and two contexts may be used in turn by one thread).
+template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx, int key) {
+    auto found = ctx->builtin.find(key);
+    if (found != ctx->builtin.end()) return *found->second;
+    PipeOps* po = new PipeOps();
+    PipeOps& ops = *po;
     using PI = PipeInfo<P>;
     constexpr bool DEFER = P::HAS_FRAGMENT && P::BLEND_IGNORES_OLD;
     ops.rec_bytes = RecLayout<P>::BYTES;
@@ -390,8 +509,8 @@ template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx) 
         if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
         else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
     };
-    ops.resident = [](bool msaa) -> int {
-        static int res[2] = {0, 0};
+    ops.resident = [po](bool msaa) -> int {
+        int* res = po->resident_cache;
         if (!res[msaa]) {
             auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
             const size_t smem = raster_smem_bytes<P, DEFER>();
@@ -402,22 +521,56 @@ template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx) 
         }
         return res[msaa];
     };
-    bound = ctx;
+    ctx->builtin[key] = po;
     return ops;
 }
 
 template <class P, bool LINES = false> int render_typed(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_tiles) {
-    return render_driver(ctx, rc, prm, n_tiles, builtin_ops<P, LINES>(ctx));
+    return render_driver(ctx, rc, prm, n_tiles, builtin_ops<P, LINES>(ctx, rc.desc->pipeline_id * 2 + (LINES ? 1 : 0)));
 }
 
 }  // namespace
 #include "runtime_pipeline.inc"
 namespace {
 
-int render_common(euc_ctx* ctx, const RenderCall& rc) {
+// Error of an earlier asynchronous render, if the host has learnt of one: reported (once) by the next call.
+int take_deferred(euc_ctx* ctx) {
+    poll_summary(ctx);
+    if (ctx->deferred_code == EUC_OK) return EUC_OK;
+    const int c = ctx->deferred_code;
+    ctx->deferred_code = EUC_OK;
+    return fail(ctx, c, "%s", ctx->deferred_msg.c_str());
+}
+
+// Pinned staging for the per-draw tables of a batch (two slots, used in turn): the copies to the device are then truly
+// asynchronous; a slot is rewritten only after the copy that last read it has finished, so the host runs up to two
+// batches ahead of the device.  Returns the slot's base address in *out.
+int stage_tables(euc_ctx* ctx, const void* a, size_t na, const void* b, size_t nb, size_t b_off, uint8_t** out) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &st);
+    if (st != cudaStreamCaptureStatusNone) return fail(ctx, EUC_E_UNSUPPORTED, "multi-draw renders stage their tables through the host and cannot be captured into a CUDA graph");
+    const int k = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    const size_t total = b_off + nb;
+    if (ctx->stage_ev[k] && ctx->stage_used[k]) CU(cudaEventSynchronize(ctx->stage_ev[k]));
+    if (total > ctx->stage_cap[k]) {
+        if (ctx->stage_host[k]) { CU(cudaFreeHost(ctx->stage_host[k])); ctx->stage_host[k] = nullptr; ctx->stage_cap[k] = 0; }
+        CU(cudaMallocHost(&ctx->stage_host[k], total + total / 2 + 4096));
+        ctx->stage_cap[k] = total + total / 2 + 4096;
+    }
+    if (!ctx->stage_ev[k]) CU(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    if (na) std::memcpy(ctx->stage_host[k], a, na);
+    if (nb) std::memcpy((uint8_t*)ctx->stage_host[k] + b_off, b, nb);
+    *out = (uint8_t*)ctx->stage_host[k];
+    return EUC_OK;
+}
+
+int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
     ctx->last = euc_render_stats{};  // a render that returns before launching anything (quirks, empty targets) reports zeros
     ctx->stats_on_device = false;
+    RenderCall rc = rc_in;
     if (!rc.desc || !rc.geom) return fail(ctx, EUC_E_INVALID, "null desc/geom");
+    { const int dc = take_deferred(ctx); if (dc != EUC_OK) return dc; }
     const euc_pipeline_desc& d = *rc.desc;
     const UserPipe* user_pipe = nullptr;
     if (d.pipeline_id >= EUC_PIPE_USER_BASE) {
@@ -483,16 +636,23 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     if (h / group_rows == 0) return plain_clear(true, true);  // needed_threads == 0: the reference renders nothing (pipeline.rs:330,337)
 
     uint32_t row_begin = rc.row_begin, row_end = std::min(rc.row_end, h);
+    if (row_begin >= row_end) return plain_clear(true, true);  // an empty band (a rank beyond the last tile row) renders nothing
     if (row_begin % TILE) return fail(ctx, EUC_E_INVALID, "row_begin must be a multiple of %d", TILE);
-    if (row_begin >= row_end) return plain_clear(true, true);
 
     // draws
     std::vector<DrawDev> dd(rc.n_draws);
     uint64_t tri_total = 0;
     const uint32_t stream_len = rc.geom->idx ? rc.geom->n_idx : rc.geom->n_verts;
+    const Geom& gm = *rc.geom;
     for (uint32_t i = 0; i < rc.n_draws; ++i) {
         const euc_batch_draw& b = rc.draws[i];
         if ((uint64_t)b.first + b.count > stream_len) return fail(ctx, EUC_E_OUT_OF_BOUNDS, "draw %u reads past the end of the vertex stream", i);
+        // can this draw read a vertex out of range?  (index.rs:53 panics; here: EUC_E_OUT_OF_BOUNDS from a checked render)
+        if (b.count) {
+            const int64_t lo = gm.idx ? (int64_t)gm.idx_min : (int64_t)b.first, hi = gm.idx ? (int64_t)gm.idx_max : (int64_t)b.first + b.count - 1;
+            const bool known = gm.idx ? gm.bounds_known : true;
+            if (known && (lo + b.base_vertex < 0 || hi + b.base_vertex >= (int64_t)gm.n_verts)) rc.maybe_oob_sync = true;
+        }
         if (b.layer >= layers) return fail(ctx, EUC_E_INVALID, "draw %u targets layer %u of %u", i, b.layer, layers);
         // primitives per draw; a trailing partial primitive is dropped (pipeline.rs:283).  LineTriangleList turns every
         // collected triangle into three lines (primitives.rs:56-76).
@@ -563,17 +723,29 @@ int render_common(euc_ctx* ctx, const RenderCall& rc) {
     }
 
     int rcode;
-    if ((rcode = ensure(ctx, ctx->draws, dd.size() * sizeof(DrawDev))) != EUC_OK) return rcode;
-    CU(cudaMemcpyAsync(ctx->draws.p, dd.data(), dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
-    prm.draws = (const DrawDev*)ctx->draws.p;
+    prm.draw0 = dd[0];
+    prm.draws = nullptr;
+    const size_t draw_bytes = dd.size() * sizeof(DrawDev), draw_pad = (draw_bytes + 255) / 256 * 256;
+    const bool batch_uniforms = rc.batch && d.uniform_bytes != 0 && rc.uniforms;
+    const size_t ub = batch_uniforms ? (size_t)d.uniform_bytes * rc.n_draws : 0;
+    if (batch_uniforms && (d.uniform_bytes & 15u)) return fail(ctx, EUC_E_INVALID, "batch uniform blocks must be a multiple of 16 bytes");
+    if (rc.n_draws > 1 || batch_uniforms) {
+        // per-draw tables go through pinned staging: asynchronous copies, one for the draws, one for the uniform blocks
+        if ((rcode = ensure(ctx, ctx->draws, draw_bytes)) != EUC_OK) return rcode;
+        if (ub && (rcode = ensure(ctx, ctx->uniforms, ub)) != EUC_OK) return rcode;
+        uint8_t* stg = nullptr;
+        const int slot = ctx->stage_next;
+        if ((rcode = stage_tables(ctx, dd.data(), draw_bytes, batch_uniforms ? rc.uniforms : nullptr, ub, draw_pad, &stg)) != EUC_OK) return rcode;
+        CU(cudaMemcpyAsync(ctx->draws.p, stg, draw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (ub) CU(cudaMemcpyAsync(ctx->uniforms.p, stg + draw_pad, ub, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+        ctx->stage_used[slot] = true;
+        prm.draws = (const DrawDev*)ctx->draws.p;
+    }
     if (rc.batch) {
-        if (d.uniform_bytes == 0 || !rc.uniforms) {
+        if (!batch_uniforms) {
             prm.uniforms = nullptr;
         } else {
-            const size_t ub = (size_t)d.uniform_bytes * rc.n_draws;
-            if ((d.uniform_bytes & 15u)) return fail(ctx, EUC_E_INVALID, "batch uniform blocks must be a multiple of 16 bytes");
-            if ((rcode = ensure(ctx, ctx->uniforms, ub)) != EUC_OK) return rcode;
-            CU(cudaMemcpyAsync(ctx->uniforms.p, rc.uniforms, ub, cudaMemcpyHostToDevice, ctx->stream));
             prm.uniforms = (const uint8_t*)ctx->uniforms.p;
             prm.uniform_stride = d.uniform_bytes;
         }
@@ -625,11 +797,16 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
     ctx->dev = device_ordinal;
     if (cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     ctx->stream = ctx->own;
-    if (cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost(&ctx->counters_host, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->counters, CTR_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->counters, 0, CTR_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->counters_host, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->summary, 8 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->summary_dev, (void*)ctx->summary, 0) != cudaSuccess) {
         delete ctx;
         return EUC_E_CUDA;
     }
+    for (int i = 0; i < 8; ++i) ctx->summary[i] = 0;
+    if (const char* e = getenv("EUC_ASYNC")) ctx->async = atoi(e) != 0;
     if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
@@ -639,17 +816,22 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
     return EUC_OK;
 }
 
+int euc_group_destroy(euc_ctx* ctx);
+
 int euc_shutdown(euc_ctx* ctx) {
     if (!ctx) return EUC_E_INVALID;
     cudaSetDevice(ctx->dev);
+    if (ctx->group) euc_group_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->bufs) { if (kv.second.ipc) cudaIpcCloseMemHandle(kv.second.d); else if (kv.second.owned) cudaFree(kv.second.d); }
     drain_profile(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->geoms) if (kv.second.owned) { cudaFree(kv.second.verts); cudaFree(kv.second.idx); }
-    Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner};
+    Scratch* ss[] = {&ctx->recs, &ctx->bbox, &ctx->tile_count, &ctx->tile_range, &ctx->tile_list, &ctx->draws, &ctx->uniforms, &ctx->tmp_verts, &ctx->tmp_idx, &ctx->winner,
+                     &ctx->ovf, &ctx->ext};
     for (Scratch* s : ss) cudaFree(s->p);
     for (auto& kv : ctx->tickets) cudaEventDestroy(kv.second);
+    for (auto& kv : ctx->builtin) delete kv.second;
     if (ctx->user) {
         for (auto& kv : ctx->user->pipes) { if (rt_api().ok) rt_api().ModuleUnload(kv.second->mod); delete kv.second; }
         delete ctx->user;
@@ -659,6 +841,8 @@ int euc_shutdown(euc_ctx* ctx) {
     cudaStreamDestroy(ctx->aux);
     cudaFree(ctx->counters);
     cudaFreeHost(ctx->counters_host);
+    if (ctx->summary) cudaFreeHost((void*)ctx->summary);
+    for (int k = 0; k < 2; ++k) { if (ctx->stage_host[k]) cudaFreeHost(ctx->stage_host[k]); if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]); }
     cudaStreamDestroy(ctx->own);
     delete ctx;
     return EUC_OK;
@@ -668,7 +852,7 @@ const char* euc_last_error(euc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null
 
 int euc_set_stream(euc_ctx* ctx, void* cuda_stream) {
     if (!ctx) return EUC_E_INVALID;
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
     return EUC_OK;
@@ -676,9 +860,18 @@ int euc_set_stream(euc_ctx* ctx, void* cuda_stream) {
 
 int euc_sync(euc_ctx* ctx) {
     if (!ctx) return EUC_E_INVALID;
+    DeviceGuard dg(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
+    return take_deferred(ctx);  // an error a finished asynchronous render left behind
+}
+
+int euc_set_async(euc_ctx* ctx, int enabled) {
+    if (!ctx) return EUC_E_INVALID;
+    ctx->async = enabled != 0;
     return EUC_OK;
 }
+
+uint64_t euc_blocking_waits(euc_ctx* ctx) { return ctx ? ctx->blocking_waits : 0; }
 
 int euc_set_stats(euc_ctx* ctx, int enabled) {
     if (!ctx) return EUC_E_INVALID;
@@ -688,10 +881,14 @@ int euc_set_stats(euc_ctx* ctx, int enabled) {
 
 int euc_get_stats(euc_ctx* ctx, euc_render_stats* out) {
     if (!ctx || !out) return EUC_E_INVALID;
+    DeviceGuard dg(ctx);
     if (ctx->stats_on_device) {
         CU(cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        ctx->last.binned_pairs = ctx->counters_host[0];
         ctx->last.fragments = ctx->counters_host[1];
+        const int dc = take_deferred(ctx);
+        if (dc != EUC_OK) return dc;
     }
     *out = ctx->last;
     return EUC_OK;
@@ -701,7 +898,7 @@ int euc_buf_create(euc_ctx* ctx, uint32_t width, uint32_t height, uint32_t layer
     if (!ctx || !out) return EUC_E_INVALID;
     if (texel_bytes != 4) return fail(ctx, EUC_E_UNSUPPORTED, "only 4-byte texels (u32 colour, f32 depth, RGBA8 texture) are supported");
     if (layers == 0) return fail(ctx, EUC_E_INVALID, "layers must be >= 1");
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     Buf b;
     b.w = width; b.h = height; b.layers = layers; b.texel = texel_bytes;
     b.bytes = (size_t)width * height * layers * texel_bytes;  // Buffer::fill_with: len = product of sizes (buffer.rs:74-75)
@@ -733,6 +930,7 @@ int euc_set_profiling(euc_ctx* ctx, int enabled) {
 
 int euc_get_profile(euc_ctx* ctx, float* ms, uint64_t* calls, int reset) {
     if (!ctx) return EUC_E_INVALID;
+    DeviceGuard dg(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     drain_profile(ctx);
     for (int s = 0; s < EUC_STAGE_COUNT; ++s) {
@@ -749,6 +947,7 @@ int euc_buf_destroy(euc_ctx* ctx, euc_buf buf) {
     if (!ctx) return EUC_E_INVALID;
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    DeviceGuard dg(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     if (it->second.ipc) CU(cudaIpcCloseMemHandle(it->second.d));
     else if (it->second.d && it->second.owned) CU(cudaFree(it->second.d));
@@ -761,16 +960,10 @@ int euc_buf_clear(euc_ctx* ctx, euc_buf buf, const void* texel) {
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     const Buf& b = it->second;
-    const size_t n = b.bytes / 4;
-    if (n == 0) return EUC_OK;
     uint32_t v;
     std::memcpy(&v, texel, 4);
-    const size_t vec = (n + 3) / 4;
-    const unsigned blocks = (unsigned)std::min<size_t>((vec + 255) / 256, (size_t)ctx->sm_count * 16);
-    ++ctx->launches;
-    fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)b.d, n, v);
-    CU(cudaGetLastError());
-    return EUC_OK;
+    DeviceGuard dg(ctx);
+    return clear_rows_impl(ctx, b, v, 0, b.h);
 }
 
 int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t row_begin, uint32_t row_end) {
@@ -779,7 +972,7 @@ int euc_buf_clear_rows(euc_ctx* ctx, euc_buf buf, const void* texel, uint32_t ro
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     uint32_t v;
     std::memcpy(&v, texel, 4);
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     return clear_rows_impl(ctx, it->second, v, row_begin, row_end);
 }
 
@@ -796,6 +989,7 @@ int euc_buf_upload(euc_ctx* ctx, euc_buf buf, const void* host, size_t bytes) {
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "upload of %zu bytes into a buffer of %zu bytes", bytes, it->second.bytes);
+    DeviceGuard dg(ctx);
     if (bytes) CU(cudaMemcpyAsync(it->second.d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return EUC_OK;
 }
@@ -805,20 +999,22 @@ int euc_buf_download(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes) {
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "download of %zu bytes from a buffer of %zu bytes", bytes, it->second.bytes);
+    DeviceGuard dg(ctx);
     if (bytes) CU(cudaMemcpyAsync(host, it->second.d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return EUC_OK;
+    return take_deferred(ctx);  // the bytes are there; an error means an earlier asynchronous render did not draw
 }
 
 int euc_host_alloc(euc_ctx* ctx, size_t bytes, void** out_ptr) {
     if (!ctx || !out_ptr) return EUC_E_INVALID;
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     CU(cudaMallocHost(out_ptr, std::max<size_t>(bytes, 1)));
     return EUC_OK;
 }
 
 int euc_host_free(euc_ctx* ctx, void* ptr) {
     if (!ctx) return EUC_E_INVALID;
+    DeviceGuard dg(ctx);
     if (ptr) CU(cudaFreeHost(ptr));
     return EUC_OK;
 }
@@ -828,6 +1024,7 @@ int euc_buf_download_async(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes, 
     auto it = ctx->bufs.find(buf);
     if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
     if (bytes != it->second.bytes) return fail(ctx, EUC_E_SIZE_MISMATCH, "download of %zu bytes from a buffer of %zu bytes", bytes, it->second.bytes);
+    DeviceGuard dg(ctx);
     if (bytes) CU(cudaMemcpyAsync(host, it->second.d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEvent_t ev = nullptr;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -844,10 +1041,11 @@ int euc_ticket_wait(euc_ctx* ctx, uint64_t ticket) {
     if (it == ctx->tickets.end()) return fail(ctx, EUC_E_INVALID, "unknown or already consumed ticket");
     cudaEvent_t ev = it->second;
     ctx->tickets.erase(it);
+    DeviceGuard dg(ctx);
     cudaError_t e = cudaEventSynchronize(ev);
     cudaEventDestroy(ev);
     if (e != cudaSuccess) return fail(ctx, EUC_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
-    return EUC_OK;
+    return take_deferred(ctx);
 }
 
 int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes) {
@@ -872,7 +1070,7 @@ int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* 
 int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, uint32_t n_vertices, const uint32_t* indices,
                     uint32_t n_indices, euc_geom* out) {
     if (!ctx || !out || (!vertices && n_vertices) || vertex_stride == 0) return EUC_E_INVALID;
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     Geom g;
     g.stride = vertex_stride; g.n_verts = n_vertices; g.n_idx = indices ? n_indices : 0;
     const size_t vb = (size_t)vertex_stride * n_vertices;
@@ -881,6 +1079,8 @@ int euc_geom_create(euc_ctx* ctx, const void* vertices, uint32_t vertex_stride, 
     if (indices) {
         CU(cudaMalloc((void**)&g.idx, std::max<size_t>((size_t)n_indices * 4, 16)));
         if (n_indices) CU(cudaMemcpyAsync(g.idx, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
+        index_bounds(indices, n_indices, g.idx_min, g.idx_max);  // once per geometry: its renders then need no host check
+        g.bounds_known = true;
     }
     CU(cudaStreamSynchronize(ctx->stream));
     uint64_t hnd = ctx->next_handle++;
@@ -907,11 +1107,50 @@ int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uin
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
     Geom& g = it->second;
+    DeviceGuard dg(ctx);
     if (vertices && g.n_verts) CU(cudaMemcpyAsync(g.verts, vertices, (size_t)g.stride * g.n_verts, cudaMemcpyHostToDevice, ctx->stream));
     if (indices) {
         if (!g.idx) return fail(ctx, EUC_E_INVALID, "geometry has no index buffer");
         if (g.n_idx) CU(cudaMemcpyAsync(g.idx, indices, (size_t)g.n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+        // large index arrays are not re-scanned per update (a frame loop re-uploading its geometry must not pay a host pass
+        // over it): the device checks every index and an out-of-range one is reported by a later call (euc_set_async)
+        g.bounds_known = g.n_idx <= HOST_SCAN_MAX_INDICES;
+        if (g.bounds_known) index_bounds(indices, g.n_idx, g.idx_min, g.idx_max);
     }
+    return EUC_OK;
+}
+
+int euc_geom_update_range(euc_ctx* ctx, euc_geom geom, const void* vertices, uint32_t first_vertex, uint32_t n_vertices, const uint32_t* indices,
+                          uint32_t first_index, uint32_t n_indices) {
+    if (!ctx) return EUC_E_INVALID;
+    auto it = ctx->geoms.find(geom);
+    if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    Geom& g = it->second;
+    if ((uint64_t)first_vertex + n_vertices > g.n_verts || (uint64_t)first_index + n_indices > g.n_idx) return fail(ctx, EUC_E_OUT_OF_BOUNDS, "range past the end of the geometry");
+    DeviceGuard dg(ctx);
+    if (vertices && n_vertices) CU(cudaMemcpyAsync(g.verts + (size_t)first_vertex * g.stride, vertices, (size_t)n_vertices * g.stride, cudaMemcpyHostToDevice, ctx->stream));
+    if (indices && n_indices) {
+        CU(cudaMemcpyAsync(g.idx + first_index, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
+        g.bounds_known = false;  // a part of the indices changed: the device checks (deferred error, see euc_set_async)
+    }
+    return EUC_OK;
+}
+
+int euc_buf_download_rows_async(euc_ctx* ctx, euc_buf buf, void* host, uint32_t row_begin, uint32_t row_end, uint64_t* out_ticket) {
+    if (!ctx || !host || !out_ticket) return EUC_E_INVALID;
+    auto it = ctx->bufs.find(buf);
+    if (it == ctx->bufs.end()) return fail(ctx, EUC_E_INVALID, "unknown buffer handle");
+    const Buf& b = it->second;
+    if (b.layers != 1) return fail(ctx, EUC_E_UNSUPPORTED, "row ranges are read back from single-layer buffers");
+    row_end = std::min(row_end, b.h);
+    DeviceGuard dg(ctx);
+    if (row_begin < row_end && b.w) CU(cudaMemcpyAsync(host, (const uint8_t*)b.d + (size_t)row_begin * b.w * 4, (size_t)(row_end - row_begin) * b.w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, ctx->stream));
+    const uint64_t t = ctx->next_ticket++;
+    ctx->tickets[t] = ev;
+    *out_ticket = t;
     return EUC_OK;
 }
 
@@ -919,6 +1158,7 @@ int euc_geom_destroy(euc_ctx* ctx, euc_geom geom) {
     if (!ctx) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
+    DeviceGuard dg(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     if (it->second.owned) {
         CU(cudaFree(it->second.verts));
@@ -934,7 +1174,7 @@ int euc_render_geom_rows(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom g
     if (!ctx || !desc) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     const Geom& g = it->second;
     euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
     RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end};
@@ -957,7 +1197,7 @@ int euc_buf_ipc_export(euc_ctx* ctx, euc_buf buf, void* handle_out) {
 int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_t height, uint32_t layers, uint32_t texel_bytes, euc_buf* out) {
     if (!ctx || !handle || !out) return EUC_E_INVALID;
     if (texel_bytes != 4 || layers == 0) return fail(ctx, EUC_E_UNSUPPORTED, "only 4-byte texels, layers >= 1");
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, sizeof h);
     void* ptr = nullptr;
@@ -977,7 +1217,7 @@ int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, e
     if (!ctx || !desc || (n_mirrors && !mirrors)) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     const Geom& g = it->second;
     euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
     RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, row_begin, row_end, mirrors, n_mirrors};
@@ -986,7 +1226,7 @@ int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, e
 
 int euc_pipeline_register(euc_ctx* ctx, const char* source, const char* struct_name, int32_t* out_pipeline_id) {
     if (!ctx || !source || !struct_name || !out_pipeline_id) return EUC_E_INVALID;
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     if (!ctx->user) ctx->user = new euc_user_pipes();
     return register_pipeline(ctx, *ctx->user, source, struct_name, out_pipeline_id);
 }
@@ -1002,7 +1242,7 @@ int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices
                const uint32_t* indices, uint32_t n_indices, euc_buf pixel, euc_buf depth) {
     DropClear drop_clear{ctx};
     if (!ctx || !desc || (!vertices && n_vertices) || vertex_stride == 0) return EUC_E_INVALID;
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     int rcode;
     const size_t vb = (size_t)vertex_stride * n_vertices;
     if ((rcode = ensure(ctx, ctx->tmp_verts, std::max<size_t>(vb, 16))) != EUC_OK) return rcode;
@@ -1013,6 +1253,8 @@ int euc_render(euc_ctx* ctx, const euc_pipeline_desc* desc, const void* vertices
         if ((rcode = ensure(ctx, ctx->tmp_idx, std::max<size_t>((size_t)n_indices * 4, 16))) != EUC_OK) return rcode;
         if (n_indices) CU(cudaMemcpyAsync(ctx->tmp_idx.p, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
         g.idx = (uint32_t*)ctx->tmp_idx.p; g.n_idx = n_indices;
+        g.bounds_known = n_indices <= HOST_SCAN_MAX_INDICES;
+        if (g.bounds_known) index_bounds(indices, n_indices, g.idx_min, g.idx_max);
     }
     euc_batch_draw one{0, g.idx ? g.n_idx : g.n_verts, 0, 0};
     RenderCall rc{desc, &g, &one, 1, desc->uniforms, false, pixel, depth, 0, 0xffffffffu};
@@ -1025,9 +1267,11 @@ int euc_render_batch(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom,
     if (!ctx || !desc || (!draws && n_draws)) return EUC_E_INVALID;
     auto it = ctx->geoms.find(geom);
     if (it == ctx->geoms.end()) return fail(ctx, EUC_E_INVALID, "unknown geometry handle");
-    CU(cudaSetDevice(ctx->dev));
+    DeviceGuard dg(ctx);
     RenderCall rc{desc, &it->second, draws, n_draws, uniforms, true, pixel, depth, 0, 0xffffffffu};
     return render_common(ctx, rc);
 }
 
 }  // extern "C"
+
+#include "group.inc"

@@ -80,7 +80,8 @@ struct Params {
     const uint8_t* vertices;
     uint32_t vstride, n_vertices;
     const uint32_t* indices;
-    const DrawDev* draws;
+    const DrawDev* draws;   // n_draws > 1: device table
+    DrawDev draw0;          // n_draws == 1: the draw itself (no table, no upload: a render is then pure kernel launches)
     uint32_t n_draws;
     uint32_t n_tris;
     const uint8_t* uniforms;  // device array of n_draws blocks (batch) or nullptr -> uni_inline
@@ -96,7 +97,19 @@ struct Params {
     uint32_t cta_bin;       // 1: primitives covering > 256 tiles are binned by the whole CTA (few, huge primitives)
     uint32_t sparse_recs;   // 1: live records are stored by their own lanes (row-restricted renders drop most primitives)
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
-    unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags
+    // Bin overflow handled on the device (renders that never wait for the host): a pair that does not fit its tile's bin
+    // goes to `ovf` (tile, primitive); the raster warp of such a tile collects its pairs into a slice of `ext`.
+    // ovf_cap == 0: an overflowing bin flags the render instead (bit 1) and the host redoes it on the exact path.
+    uint2* ovf;
+    uint32_t* ext;
+    uint32_t ovf_cap;
+    // Render summary for the host, written by the last raster warp into mapped pinned memory (no host call needed to
+    // learn it): [0] sequence number (written last), [1] flags, [2] longest tile list, [3] overflow pairs, [4] pairs,
+    // [5] tiles of the render
+    volatile unsigned long long* summary;
+    unsigned long long seq;
+    unsigned long long* counters;  // [0] pairs, [1] fragments, [2] list cursor, [3] error flags, [4] tile ticket, [5] overflow
+                                   // pairs, [6] ext cursor | warps done << 32, [7] longest tile list
     int32_t stats;
     SamplerDev samp[EUC_MAX_SAMPLERS];
     alignas(16) uint8_t uni_inline[320];
@@ -106,18 +119,42 @@ struct Params {
 // K7 clear
 // -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, size_t n, uint32_t v) {
+    // scalar head up to the first 16-byte boundary (a row range of a target whose width is not a multiple of 4), 128-bit
+    // body, scalar tail; head and tail are written by the first threads of block 0
+    const size_t head = min(n, (size_t)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2));
+    uint32_t* const body = dst + head;
+    const size_t nb = n - head;
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    size_t stride = (size_t)gridDim.x * blockDim.x * 4;
-    uint4 vv = make_uint4(v, v, v, v);
-    for (; i + 4 <= n; i += stride) *reinterpret_cast<uint4*>(dst + i) = vv;
-    // tail (n % 4) handled by the last few threads of block 0
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n & ~(size_t)3) + threadIdx.x] = v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    const uint4 vv = make_uint4(v, v, v, v);
+    for (; i + 4 <= nb; i += stride) *reinterpret_cast<uint4*>(body + i) = vv;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) dst[threadIdx.x] = v;
+        if (threadIdx.x < (nb & 3)) body[(nb & ~(size_t)3) + threadIdx.x] = v;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------------
 // tile traversal shared by the count and fill passes
 // -------------------------------------------------------------------------------------------------------
 struct TileRect { uint32_t tx0, ty0, ntx, nty, layer_base; };
+
+// Error / abort flags of a render (counters[3])
+constexpr unsigned long long FLAG_OOB = 1ull;       // a vertex index was out of range
+constexpr unsigned long long FLAG_BINS = 2ull;      // a bin (or the pair list of the exact path) was too small: the host redoes the render
+constexpr unsigned long long FLAG_OVF_FULL = 4ull;  // the overflow buffer itself was too small: the render is dropped
+
+// Fast-path append of (tile <- primitive) when slot `sl` of the tile's bin has been taken.
+__device__ __forceinline__ void bin_store(const Params& p, uint32_t tile, uint32_t sl, uint32_t tri, bool& over) {
+    if (sl < p.bin_cap) {
+        p.tile_list[(size_t)tile * p.bin_cap + sl] = tri;
+    } else if (p.ovf_cap) {
+        const unsigned long long k = atomicAdd(p.counters + 5, 1ull);
+        if (k < (unsigned long long)p.ovf_cap) p.ovf[k] = make_uint2(tile, tri); else over = true;
+    } else {
+        over = true;
+    }
+}
 
 __device__ __forceinline__ bool tile_rect(const Params& p, uint2 bb, uint32_t layer, TileRect& r) {
     uint32_t x0 = bb.x & 0xffffu, x1 = bb.x >> 16, y0 = bb.y & 0xffffu, y1 = bb.y >> 16;
@@ -196,6 +233,8 @@ __device__ __forceinline__ uint32_t find_draw(const Params& p, uint32_t tri) {
     return lo;
 }
 
+__device__ __forceinline__ DrawDev draw_of(const Params& p, uint32_t d) { return p.n_draws == 1 ? p.draw0 : p.draws[d]; }
+
 template <class P> __device__ __forceinline__ const typename P::Uniforms& uniforms_of(const Params& p, uint32_t draw) {
     const uint8_t* base = p.uniforms ? p.uniforms + (size_t)draw * p.uniform_stride : p.uni_inline;
     return *reinterpret_cast<const typename P::Uniforms*>(base);
@@ -254,7 +293,7 @@ __device__ __forceinline__ void bin_big_warp(const Params& p, bool big, const Ti
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (base + (uint32_t)k * 32u + lane < total) {
-                if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = id[k]; else over = true;
+                bin_store(p, tl[k], sl[k], id[k], over);
             }
         }
     }
@@ -298,7 +337,7 @@ __device__ __forceinline__ bool bin_huge_cta(const Params& p, bool huge, const T
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (base + (uint32_t)k * blockDim.x + threadIdx.x < a.w) {
-                    if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = b.y; else over = true;
+                    bin_store(p, tl[k], sl[k], b.y, over);
                 }
             }
         }
@@ -325,7 +364,7 @@ template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) se
 
     if (live) {
         const uint32_t d = find_draw(p, tri);
-        const DrawDev dr = p.draws[d];
+        const DrawDev dr = draw_of(p, d);
         layer = dr.layer;
         const typename P::Uniforms& u = uniforms_of<P>(p, d);
         const uint32_t s0 = dr.first + 3u * (tri - dr.tri_begin);
@@ -530,7 +569,7 @@ template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) se
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if (k0 + (uint32_t)k < nt) {
-                        if (sl[k] < p.bin_cap) p.tile_list[(size_t)tl[k] * p.bin_cap + sl[k]] = tri; else over = true;
+                        bin_store(p, tl[k], sl[k], tri, over);
                     }
                 }
             }
@@ -541,7 +580,7 @@ template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) se
             if (bin_huge_cta(p, big && nt > 256u, r, nt, tri, over, npairs)) big = false;
         }
         bin_big_warp(p, big, r, nt, tri, over, npairs);
-        if (over) atomicOr(p.counters + 3, 2ull);
+        if (over) atomicOr(p.counters + 3, p.ovf_cap ? FLAG_OVF_FULL : FLAG_BINS);
     } else {
         for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
     }
@@ -586,7 +625,7 @@ template <class P> __global__ void __launch_bounds__(128) setup_lines_kernel(con
     bool oob = false;
     if (live) {
         const uint32_t d = find_draw(p, li);
-        const DrawDev dr = p.draws[d];
+        const DrawDev dr = draw_of(p, d);
         layer = dr.layer;
         const typename P::Uniforms& u = uniforms_of<P>(p, d);
         const uint32_t l0 = li - dr.tri_begin;
@@ -662,11 +701,10 @@ template <class P> __global__ void __launch_bounds__(128) setup_lines_kernel(con
     if (p.bin_cap) {
         bool over = false;
         for_each_tile(p, valid, r, li, [&](uint32_t tile, uint32_t t) {
-            const uint32_t slot = atomicAdd(p.tile_count + tile, 1u);
-            if (slot < p.bin_cap) p.tile_list[(size_t)tile * p.bin_cap + slot] = t; else over = true;
+            bin_store(p, tile, atomicAdd(p.tile_count + tile, 1u), t, over);
             ++npairs;
         });
-        if (over) atomicOr(p.counters + 3, 2ull);
+        if (over) atomicOr(p.counters + 3, p.ovf_cap ? FLAG_OVF_FULL : FLAG_BINS);
     } else {
         for_each_tile(p, valid, r, li, [&](uint32_t tile, uint32_t) { atomicAdd(p.tile_count + tile, 1u); ++npairs; });
     }
@@ -700,14 +738,14 @@ __global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant_
 
 // Non-zero when this render must not proceed: a vertex index was out of range (bit 0) or the pair list is too small
 // (bit 1).  Written before fill/raster start (stream order); the host re-launches them after growing the list.
-__device__ __forceinline__ bool render_aborted(const Params& p) { return (*(volatile unsigned long long*)(p.counters + 3) & 3ull) != 0ull; }
+__device__ __forceinline__ bool render_aborted(const Params& p) { return (*(volatile unsigned long long*)(p.counters + 3) & (FLAG_OOB | FLAG_BINS | FLAG_OVF_FULL)) != 0ull; }
 
 __global__ void __launch_bounds__(128) fill_kernel(const __grid_constant__ Params p) {
     if (render_aborted(p)) return;
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = tri < p.n_tris;
     uint2 bbox = live ? p.tri_bbox[tri] : make_uint2(0u, 0u);
-    const uint32_t layer = live ? p.draws[find_draw(p, tri)].layer : 0u;
+    const uint32_t layer = live ? draw_of(p, find_draw(p, tri)).layer : 0u;
     TileRect r;
     bool valid = live && tile_rect(p, bbox, layer, r);
     for_each_tile(p, valid, r, tri, [&](uint32_t tile, uint32_t t) {
@@ -859,9 +897,11 @@ template <class P, bool DEFER> struct StageGeom {
     static constexpr uint32_t WORDS = BATCHES * BATCH * REC_WORDS;                                           // stage words per warp
 };
 
-template <class P, bool DEFER> constexpr size_t raster_smem_bytes() {
-    return (size_t)RASTER_WARPS * (StageGeom<P, DEFER>::WORDS * 4 + 16 + 32 * (Q_STRIDE_WORDS + COL_STRIDE) * 4);
-}
+// per warp: record stage | 16 B (mbarriers) | per-lane fragment queues | per-lane colour rows
+template <class P, bool DEFER> struct WarpSmem {
+    static constexpr uint32_t BYTES = StageGeom<P, DEFER>::WORDS * 4u + 16u + ((!DEFER && P::HAS_FRAGMENT) ? 32u * (Q_STRIDE_WORDS + COL_STRIDE) * 4u : 0u);
+};
+template <class P, bool DEFER> constexpr size_t raster_smem_bytes() { return (size_t)RASTER_WARPS * WarpSmem<P, DEFER>::BYTES; }
 
 // interpolate() reading the setup record from shared memory with 128-bit loads (lanes address different records)
 template <class P> __device__ __forceinline__ void interpolate_smem(const float4* __restrict__ rec4, float xf, float yf, float* var) {
@@ -1034,22 +1074,26 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
 // Returns (mbarrier phase after the tile, fragments emitted).
 template <class P, bool MSAA, bool DEFER, bool LINES>
 __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
-                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm) {
+                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, uint32_t& max_list) {
     using L = RecLayout<P>;
     uint32_t nfrag = 0;
     constexpr uint32_t SW = StageGeom<P, DEFER>::REC_WORDS;
     constexpr uint32_t NB = StageGeom<P, DEFER>::BATCHES;
     constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
     uint2 rg;
+    uint32_t n_bin;  // entries of the list that live in the tile's own bin / slice; the rest (bin overflow) in `ext`
     if (p.bin_cap) {
         const uint32_t cnt_t = p.tile_count[tile];
         rg = make_uint2(tile * p.bin_cap, cnt_t);
         __syncwarp();
         if (lane == 0 && cnt_t) p.tile_count[tile] = 0u;  // leave the counters zeroed for the next render
+        n_bin = min(cnt_t, p.bin_cap);
     } else {
         rg = p.tile_range[tile];
+        n_bin = rg.y;
     }
     const uint32_t n = rg.y;
+    max_list = max(max_list, n);
     if (n == 0) {
         // A tile without primitives still owes its rows to the mirrors (fused gather; immediate-mode pipelines, deferred
         // ones forward from resolve_kernel) and, under a fused clear, the clear values to its own targets.
@@ -1101,21 +1145,41 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     // Short lists: sorted element r*32+lane ends up in register v[r] of this lane, which is exactly the id this lane
     // needs when it issues the bulk copy of batch r.  Long lists are sorted in place and read back from global memory.
     const bool short_list = n <= (uint32_t)IDS_REGS;
-    uint32_t* const list = p.tile_list + rg.x;
+    uint32_t* const bin = p.tile_list + rg.x;
+    uint32_t* ext = nullptr;
+    if (n > n_bin) {
+        // The bin overflowed (warp-uniform, rare: the host sizes the bins from the lists of earlier renders).  The pairs
+        // that did not fit are somewhere in the overflow buffer: take a slice of `ext` and collect this tile's pairs.
+        uint32_t base_e = 0;
+        if (lane == 0) base_e = (uint32_t)atomicAdd(p.counters + 6, (unsigned long long)(n - n_bin));
+        ext = p.ext + __shfl_sync(0xffffffffu, base_e, 0);
+        const uint32_t K = (uint32_t)min(*(volatile unsigned long long*)(p.counters + 5), (unsigned long long)p.ovf_cap);
+        uint32_t off = 0;
+        for (uint32_t i0 = 0; i0 < K; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            const uint2 e = i < K ? p.ovf[i] : make_uint2(0xffffffffu, 0u);
+            const bool hit = e.x == tile;
+            const uint32_t b = __ballot_sync(0xffffffffu, hit);
+            if (hit) ext[off + __popc(b & ((1u << lane) - 1u))] = e.y;
+            off += __popc(b);
+        }
+        __syncwarp();
+    }
+    auto lst = [&](uint32_t i) -> uint32_t& { return i < n_bin ? bin[i] : ext[i - n_bin]; };
     uint32_t v[4];
     if (short_list) {
 #pragma unroll
-        for (uint32_t r = 0; r < 4; ++r) v[r] = r * 32 + lane < n ? list[r * 32 + lane] : 0xffffffffu;
+        for (uint32_t r = 0; r < 4; ++r) v[r] = r * 32 + lane < n ? lst(r * 32 + lane) : 0xffffffffu;
         if (n > 1) bitonic_regs128(v, lane);
     } else {
         uint32_t np2 = 1;
         while (np2 < n) np2 <<= 1;
         if (np2 <= (uint32_t)SORT_SMEM && np2 <= StageGeom<P, DEFER>::WORDS) {
             uint32_t* a = recs_sm;  // the record stages are not in use yet
-            for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? list[i] : 0xffffffffu;
+            for (uint32_t i = lane; i < np2; i += 32u) a[i] = i < n ? lst(i) : 0xffffffffu;
             __syncwarp();
             bitonic_mem(a, np2, lane);
-            for (uint32_t i = lane; i < n; i += 32u) list[i] = a[i];
+            for (uint32_t i = lane; i < n; i += 32u) lst(i) = a[i];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above, bulk-copy writes below
         } else {
             // In place in global memory, any n: the all-ascending bitonic network (first step of every merge pairs i
@@ -1123,8 +1187,8 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
             // +inf, never move below n, so pairs that reach past n are simply skipped.
             auto cmpx = [&](uint32_t i, uint32_t partner) {
                 if (partner > i && partner < n) {
-                    const uint32_t x = list[i], y2 = list[partner];
-                    if (x > y2) { list[i] = y2; list[partner] = x; }
+                    const uint32_t x = lst(i), y2 = lst(partner);
+                    if (x > y2) { lst(i) = y2; lst(partner) = x; }
                 }
             };
             for (uint32_t k = 2; k <= np2; k <<= 1) {
@@ -1141,7 +1205,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     auto batch_id = [&](uint32_t b) -> uint32_t {  // id of element b*32+lane of the sorted list (0 past the end)
         if (short_list) return b == 0 ? v[0] : (b == 1 ? v[1] : (b == 2 ? v[2] : v[3]));
         const uint32_t pos = b * BATCH + lane;
-        return pos < n ? list[pos] : 0u;
+        return pos < n ? lst(pos) : 0u;
     };
 
     // tile / lane geometry
@@ -1349,7 +1413,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
 
         uint32_t qn = 0, qf = 0;  // queued entries / fragments of this lane
         for (;;) {
-            // ---- generate: coverage + depth for this lane's own triangles, until its FIFO is nearly full ----
+            // ---- generate: coverage + depth for this lane's own triangles, until its queue is nearly full ----
             while ((own0 | own1) && qn < (uint32_t)Q_ENTRIES && qf < (uint32_t)Q_FRAGS) {
                 uint32_t t;
                 if (own0) { t = (uint32_t)__ffs((int)own0) - 1u; own0 &= own0 - 1u; }
@@ -1644,38 +1708,60 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     constexpr uint32_t STW = StageGeom<P, DEFER>::WORDS;
-    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(smem_raw) + warp * STW;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RASTER_WARPS * STW * 4) + warp * 2;
-    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)RASTER_WARPS * (STW * 4 + 16)) +
-                              warp * 32 * (Q_STRIDE_WORDS + COL_STRIDE);
+    uint8_t* const warp_sm = smem_raw + (size_t)warp * WarpSmem<P, DEFER>::BYTES;
+    uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(warp_sm);
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(warp_sm + STW * 4);
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 16);
     uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
     uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    if (render_aborted(p)) return;
-    uint32_t phase = 0, nfrag = 0;
-    unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
-    // tickets enumerate only the tile rows that intersect the rendered rows [row_begin, row_end)
-    const uint32_t ty_lo = p.row_begin / TILE, ty_hi = (min(p.row_end, p.h) + TILE - 1) / TILE;
-    const uint32_t per_layer = (ty_hi - ty_lo) * p.tiles_x, n_active = per_layer * p.layers;
-    for (;;) {
-        uint32_t tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1u);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= n_active) break;
-        const uint32_t lay = tk / per_layer;
-        const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
-        if (tile >= n_tiles) break;
-        const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm);
-        phase = res.x;
-        nfrag += res.y;
-        __syncwarp();
-    }
-    if (p.stats) {
+    uint32_t phase = 0, nfrag = 0, max_list = 0;
+    if (!render_aborted(p)) {
+        unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
+        // tickets enumerate only the tile rows that intersect the rendered rows [row_begin, row_end)
+        const uint32_t ty_lo = p.row_begin / TILE, ty_hi = (min(p.row_end, p.h) + TILE - 1) / TILE;
+        const uint32_t per_layer = (ty_hi - ty_lo) * p.tiles_x, n_active = per_layer * p.layers;
+        for (;;) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1u);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            if (tk >= n_active) break;
+            const uint32_t lay = tk / per_layer;
+            const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
+            if (tile >= n_tiles) break;
+            const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list);
+            phase = res.x;
+            nfrag += res.y;
+            __syncwarp();
+        }
+        if (p.stats) {
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) nfrag += __shfl_xor_sync(0xffffffffu, nfrag, s);
-        if (lane == 0 && nfrag) atomicAdd(p.counters + 1, (unsigned long long)nfrag);
+            for (int s = 16; s > 0; s >>= 1) nfrag += __shfl_xor_sync(0xffffffffu, nfrag, s);
+            if (lane == 0 && nfrag) atomicAdd(p.counters + 1, (unsigned long long)nfrag);
+        }
+    } else if (p.summary) {
+        // an aborted asynchronous render has no host behind it to restore the all-zero tile counters
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += gridDim.x * blockDim.x) p.tile_count[i] = 0u;
+    }
+    // Summary for the host: the last warp of the grid to get here publishes flags / longest list / overflow volume into
+    // mapped pinned memory, so that the host can size the bins of later renders without ever waiting for this one.
+    if (p.summary && lane == 0) {
+        if (max_list) atomicMax(p.counters + 7, (unsigned long long)max_list);
+        __threadfence();
+        const unsigned long long done = atomicAdd(p.counters + 8, 1ull) + 1ull;
+        if (done == (unsigned long long)gridDim.x * RASTER_WARPS) {
+            volatile unsigned long long* c = p.counters;
+            if (c[3]) atomicOr(p.counters + 15, c[3]);  // sticky until the host has seen it (several renders may finish between two looks)
+            p.summary[1] = c[15];
+            p.summary[2] = c[7];
+            p.summary[3] = c[5];
+            p.summary[4] = c[0];
+            p.summary[5] = n_tiles;
+            __threadfence_system();
+            p.summary[0] = p.seq;
+        }
     }
 }
 

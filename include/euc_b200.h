@@ -47,7 +47,7 @@ typedef unsigned long long uintptr_t;
 extern "C" {
 #endif
 
-#define EUC_B200_ABI_VERSION 1
+#define EUC_B200_ABI_VERSION 2
 
 typedef struct euc_ctx euc_ctx;
 typedef uint64_t euc_buf;  /* device Buffer2d handle; 0 == euc `Empty` target */
@@ -183,6 +183,20 @@ const char* euc_last_error(euc_ctx* ctx);
 /* Run all subsequent work of this context on `cuda_stream` (a cudaStream_t / CUstream); NULL = the context's own stream. */
 int euc_set_stream(euc_ctx* ctx, void* cuda_stream);
 int euc_sync(euc_ctx* ctx);
+/* Asynchronous renders (default: enabled).  A render call then never waits for the device: (tile, primitive) pairs that do
+ * not fit the bins sized from earlier renders are handled on the device, and what the host needs to size later renders
+ * reaches it through mapped pinned memory.  Consequences for errors that only the device can detect: a vertex index out
+ * of range in geometry whose index bounds the host has not seen (euc_geom_wrap; euc_geom_update / euc_render with more
+ * than 65536 indices) makes that render draw nothing and is reported as EUC_E_OUT_OF_BOUNDS by the NEXT call on the
+ * context (render, euc_sync, download, euc_get_stats); exhaustion of the bin-overflow buffer likewise as EUC_E_OOM (the
+ * buffer is then larger: re-issue the frame).  Geometry created with euc_geom_create, small index streams and non-indexed
+ * streams are validated on the host and fail in the render call itself, like the reference's slice-index panic
+ * (src/index.rs:53).  The first render of a target shape, and every render after euc_set_async(ctx, 0), is checked:
+ * the call waits for the set-up kernel's flags (not for the raster work).  A whole frame of asynchronous single-draw
+ * renders can be captured into a CUDA graph on the stream given to euc_set_stream. */
+int euc_set_async(euc_ctx* ctx, int enabled);
+/* Number of render calls so far that had to wait for the device (diagnostics: constant in steady state). */
+uint64_t euc_blocking_waits(euc_ctx* ctx);
 /* Enable (1) / disable (0) fragment counting; counting costs one atomic per warp per tile. */
 int euc_set_stats(euc_ctx* ctx, int enabled);
 int euc_get_stats(euc_ctx* ctx, euc_render_stats* out); /* blocking; stats of the last render call */
@@ -219,6 +233,9 @@ int euc_host_alloc(euc_ctx* ctx, size_t bytes, void** out_ptr);
 int euc_host_free(euc_ctx* ctx, void* ptr);
 int euc_buf_download_async(euc_ctx* ctx, euc_buf buf, void* host, size_t bytes, uint64_t* out_ticket);
 int euc_ticket_wait(euc_ctx* ctx, uint64_t ticket);
+/* Rows [row_begin, row_end) of a single-layer buffer into `host` (tightly packed), asynchronously: a rank of a group
+ * reads back the band it rendered. */
+int euc_buf_download_rows_async(euc_ctx* ctx, euc_buf buf, void* host, uint32_t row_begin, uint32_t row_end, uint64_t* out_ticket);
 int euc_buf_device_ptr(euc_ctx* ctx, euc_buf buf, void** out_ptr, size_t* out_bytes);
 int euc_buf_size(euc_ctx* ctx, euc_buf buf, uint32_t* w, uint32_t* h, uint32_t* layers);
 /* Wrap caller-owned device memory (e.g. a slice of a collective's receive buffer) as a Buffer2d. Not freed by destroy. */
@@ -234,6 +251,10 @@ int euc_geom_wrap(euc_ctx* ctx, void* device_vertices, uint32_t vertex_stride, u
 int euc_geom_destroy(euc_ctx* ctx, euc_geom geom);
 /* Re-upload vertices (and indices) into an existing geom of the same shape; asynchronous when the host memory is pinned. */
 int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uint32_t* indices);
+/* Re-upload a part: `vertices` holds n_vertices vertices that become vertices [first_vertex, ..), `indices` likewise
+ * (either pointer may be NULL).  With euc_group_allgather_geom: every rank uploads its own slice only. */
+int euc_geom_update_range(euc_ctx* ctx, euc_geom geom, const void* vertices, uint32_t first_vertex, uint32_t n_vertices,
+                          const uint32_t* indices, uint32_t first_index, uint32_t n_indices);
 
 /* ---- render ----------------------------------------------------------------------------------------- */
 /* Pipeline::render with host geometry: uploads, renders, returns without waiting for the device. */
@@ -259,6 +280,39 @@ int euc_buf_ipc_import(euc_ctx* ctx, const void* handle, uint32_t width, uint32_
 #define EUC_MAX_MIRRORS 7
 int euc_render_geom_rows_mirrored(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, euc_buf pixel, euc_buf depth,
                                   uint32_t row_begin, uint32_t row_end, const euc_buf* mirrors, uint32_t n_mirrors);
+/* ---- multi-GPU: one process (or host thread) per GPU of one node, one context each ------------------------------------
+ * The reference spreads the row bands of a frame over a thread pool (render_par, src/pipeline.rs:304-366; bands are
+ * independent, :340-362).  Here a band goes to a GPU.  Nothing below needs MPI, NCCL or torch: the ranks meet in a POSIX
+ * shared-memory segment named after `name`, exchange CUDA IPC handles there, and synchronise on the device through flags
+ * in each other's memory (NVLink / NVSwitch peer stores). */
+#define EUC_MAX_GROUP 8
+/* Collective over `world` ranks (blocks until all have joined; 120 s time-out).  A context belongs to at most one group. */
+int euc_group_create(euc_ctx* ctx, const char* name, uint32_t rank, uint32_t world);
+int euc_group_destroy(euc_ctx* ctx); /* collective */
+/* Collective: every rank passes one buffer of the same size (created by euc_buf_create, >= 2 MiB); peers_out[r] is rank
+ * r's buffer as mapped into this context (peers_out[own rank] == buf).  Stores into a peer's buffer travel over NVLink. */
+int euc_group_share_buf(euc_ctx* ctx, euc_buf buf, euc_buf* peers_out /* world entries */);
+/* Stream-ordered barrier on the device, no host wait: work queued on this context's stream after the call starts only when
+ * every rank's work queued before ITS call has finished and is visible (also peer stores).  Every rank must call it the
+ * same number of times.  A rank that never arrives makes the others give up after 10 s (EUC_E_CUDA from a later call). */
+int euc_group_barrier(euc_ctx* ctx);
+/* The two partitions of a job (pure arithmetic, no context): tile-aligned row bands of one large frame (ranks beyond the
+ * last tile row get the empty band [0,0)), and contiguous ranges of independent frames (sizes differ by at most one). */
+int euc_group_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* row_begin, uint32_t* row_end);
+int euc_group_frames(uint32_t n_frames, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* end);
+/* This rank's row band of one frame (euc_render_geom_rows over euc_group_rows), the band's colour rows being stored by the
+ * raster / resolve kernels into the root's framebuffer as well (EUC_GATHER_ROOT: rank 0 ends up with the whole frame, each
+ * row crosses NVLink once), into every peer's (EUC_GATHER_ALL), or nowhere else (EUC_GATHER_NONE), followed by
+ * euc_group_barrier (not for EUC_GATHER_NONE).  pixel_peers: what euc_group_share_buf returned for the colour target;
+ * depth: this rank's own depth target.  A pending euc_render_clear applies to the band.  Collective. */
+enum euc_gather { EUC_GATHER_NONE = 0, EUC_GATHER_ROOT = 1, EUC_GATHER_ALL = 2 };
+int euc_group_render(euc_ctx* ctx, const euc_pipeline_desc* desc, euc_geom geom, const euc_buf* pixel_peers, euc_buf depth, int gather);
+/* Collective: every rank holds a geometry of the same shape (euc_geom_create; arrays >= 2 MiB) and has uploaded its own
+ * 1/world slice of the vertices and of the indices (euc_geom_update_range over euc_group_frames of the two counts); each
+ * rank's slice is copied into every peer's geometry over NVLink, then euc_group_barrier.  A frame loop that re-uploads its
+ * geometry moves it over PCIe once in total instead of once per GPU. */
+int euc_group_allgather_geom(euc_ctx* ctx, euc_geom geom);
+
 /* Row N3 of SURVEY 8(f): pipelines whose shader stages are CUDA source compiled at run time (NVRTC), the device analogue
  * of writing `impl Pipeline for MyShader` in the reference (src/pipeline.rs:171-244).  `source` is placed inside
  * `namespace eucb` after the kernels of this library and must define `struct <struct_name>` with the static interface

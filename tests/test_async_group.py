@@ -1,0 +1,231 @@
+"""GPU tests of the round-2 host path: renders that never wait for the device (device-side bin overflow, deferred errors,
+CUDA-graph capture) and the multi-GPU group entry points of the C ABI, exercised with two contexts (two host threads) on
+one GPU.  Everything goes through the C ABI; the oracle is the checker."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import euc_b200 as e
+from euc_b200 import parallel, scenes
+from oracle import oracle
+from conftest import assert_colour_within_1lsb, assert_depth_bit_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def _stacked_tris(n, seed):
+    """n small triangles on the same few tiles, later ones nearer (all pass): blending makes the result order-sensitive."""
+    r = scenes.u01(seed, n * 3 * 8).reshape(n, 3, 8)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    v["pos"][:, :, 0] = -0.9 + r[:, :, 0] * 0.08
+    v["pos"][:, :, 1] = 0.2 + r[:, :, 1] * 0.6
+    v["pos"][:, :, 2] = 0.9 - 0.8 * (np.arange(n)[:, None] / n) + r[:, :, 2] * 1e-4
+    v["pos"][:, :, 3] = 1.0
+    v["rgba"][:, :, :3] = r[:, :, 3:6]
+    v["rgba"][:, :, 3] = 0.5
+    return v.reshape(-1)
+
+
+def _oracle_frame(verts, w, h, idx=None):
+    rpx, rz = np.full((h, w), 0xFF000000, np.uint32), np.full((h, w), 1.0, np.float32)
+    src = verts if idx is None else e.IndexedVertices(idx, verts)
+    st = oracle.render(e.BlendTris(), src, rpx, rz, n_threads=0)
+    return rpx, rz, st
+
+
+def test_bin_overflow_is_handled_on_the_device_without_a_host_wait():
+    ctx = e.Context(0)
+    w, h = 640, 64
+    px = e.Buffer2d([w, h], np.uint32, ctx)
+    z = e.Buffer2d([w, h], np.float32, ctx)
+    pipe = e.BlendTris()
+    # first render of this target shape: checked (the host waits for set-up), lists far below the 128-slot bins
+    pipe.render(_stacked_tris(40, 1), px, z, clear=(0xFF000000, 1.0))
+    ctx.sync()
+    waits = ctx.blocking_waits()
+    assert waits >= 1
+    for n in (700, 3000, 700):  # lists of ~n entries per tile: 128-slot bins overflow, the device collects the rest
+        v = _stacked_tris(n, 1234 + n)
+        ctx.set_stats(True)
+        pipe.render(v, px, z, clear=(0xFF000000, 1.0))
+        st = ctx.get_stats()
+        ctx.set_stats(False)
+        rpx, rz, rs = _oracle_frame(v, w, h)
+        assert st["fragments"] == rs["fragments"]
+        assert_depth_bit_exact(z.raw(), rz, f"overflow n={n}")
+        assert_colour_within_1lsb(px.raw(), rpx, f"overflow n={n}")
+    assert ctx.blocking_waits() == waits, "asynchronous renders must not wait for the device"
+    del px, z
+    ctx.close()
+
+
+def test_checked_mode_still_redoes_overflowing_renders_on_the_exact_path():
+    ctx = e.Context(0)
+    ctx.set_async(False)
+    w, h = 640, 64
+    px = e.Buffer2d([w, h], np.uint32, ctx)
+    z = e.Buffer2d([w, h], np.float32, ctx)
+    for n in (40, 900):
+        v = _stacked_tris(n, 77 + n)
+        e.BlendTris().render(v, px, z, clear=(0xFF000000, 1.0))
+        rpx, rz, _ = _oracle_frame(v, w, h)
+        assert_depth_bit_exact(z.raw(), rz, f"checked n={n}")
+        assert_colour_within_1lsb(px.raw(), rpx, f"checked n={n}")
+    assert ctx.blocking_waits() >= 2
+    del px, z
+    ctx.close()
+
+
+def test_out_of_range_index_in_unseen_indices_is_reported_by_the_next_call():
+    ctx = e.Context(0)
+    w, h = 512, 512
+    verts, idx = scenes.blend_tris(1 << 15, w, h, seed=5)   # 196608 indices: above the host-scan limit
+    geom = e.Geometry(verts, idx, ctx)
+    px = e.Buffer2d.fill([w, h], 0xFF000000, dtype=np.uint32, ctx=ctx)
+    z = e.Buffer2d.fill([w, h], 1.0, ctx=ctx)
+    pipe = e.BlendTris()
+    pipe.render(geom, px, z)                 # checked first render; bounds known from euc_geom_create
+    ctx.sync()
+    good_px, good_z = px.raw().copy(), z.raw().copy()
+    bad = idx.copy()
+    bad[1000] = verts.shape[0] + 5
+    keep = np.ascontiguousarray(bad)
+    geom.update(verts.ctypes.data, keep.ctypes.data)   # large index array: not re-scanned on the host
+    pipe.render(geom, px, z)                 # returns at once; the device finds the bad index and draws nothing
+    with pytest.raises(e.EucError) as ei:
+        ctx.sync()
+    assert ei.value.code == e.abi.E_OUT_OF_BOUNDS
+    assert np.array_equal(px.raw(), good_px) and np.array_equal(z.raw().view(np.uint32), good_z.view(np.uint32)), "the failed render must not draw"
+    # the context keeps working (tile counters were restored on the device)
+    geom.update(verts.ctypes.data, idx.ctypes.data)
+    px.clear(0xFF000000); z.clear(1.0)
+    pipe.render(geom, px, z)
+    ctx.sync()
+    rpx, rz, _ = _oracle_frame(verts, w, h, idx)
+    assert_depth_bit_exact(z.raw(), rz, "after deferred error")
+    assert_colour_within_1lsb(px.raw(), rpx, "after deferred error")
+    del px, z, geom
+    ctx.close()
+
+
+def test_whole_frame_replays_from_a_cuda_graph():
+    import torch
+    ctx = e.Context(0)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    w, h, s = 640, 480, 512
+    tp, u = scenes.teapot_stream(), scenes.teapot_uniforms(w, h, s)
+    geom = e.Geometry(tp, None, ctx)
+    shadow, color, depth = e.Buffer2d([s, s], np.float32, ctx), e.Buffer2d([w, h], np.uint32, ctx), e.Buffer2d([w, h], np.float32, ctx)
+    p1 = e.TeapotShadow(u["shadow_mvp"]).freeze()
+    p2 = e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], shadow.linear().clamped(), u["light_vp"], u["cam_pos"]).freeze()
+
+    def frame():
+        p1.render(geom, e.Empty(), shadow, clear=(None, 1.0))
+        p2.render(geom, color, depth, clear=(0, 1.0))
+
+    frame()   # checked renders: sizes the scratch buffers and verifies the bin hints
+    ctx.sync()
+    want_c, want_z, want_s = color.raw().copy(), depth.raw().copy(), shadow.raw().copy()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        frame()
+    color.clear(7); depth.clear(0.0); shadow.clear(0.0)
+    ctx.sync()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(color.raw(), want_c)
+    assert np.array_equal(depth.raw().view(np.uint32), want_z.view(np.uint32)) and np.array_equal(shadow.raw().view(np.uint32), want_s.view(np.uint32))
+    del g, geom, shadow, color, depth
+    ctx.close()
+
+
+def _two_ranks(fn):
+    """Runs fn(rank, ctx, group, sync) on two host threads, one context each on GPU 0; re-raises the first failure."""
+    name = f"t{os.getpid()}_{np.random.randint(1 << 30)}"
+    errs, host_barrier = [], threading.Barrier(2)
+
+    def worker(rank):
+        try:
+            ctx = e.Context(0)
+            grp = parallel.Group(ctx, name, rank, 2)
+            try:
+                fn(rank, ctx, grp, host_barrier)
+            finally:
+                grp.close()
+                ctx.close()
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+            host_barrier.abort()
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    if errs:
+        raise errs[0]
+
+
+@pytest.mark.parametrize("gather", ["root", "all"])
+def test_group_render_gathers_row_bands(gather):
+    w, h = 1024, 768
+    verts, idx = scenes.blend_tris(1 << 13, w, h, seed=3, size_px=(3.0, 20.0))
+    rpx, rz, _ = _oracle_frame(verts, w, h, idx)
+    frames = {}
+
+    def run(rank, ctx, grp, sync):
+        geom = e.Geometry(verts, idx, ctx)
+        color = e.Buffer2d.fill([w, h], 0x11111111, dtype=np.uint32, ctx=ctx)
+        depth = e.Buffer2d([w, h], np.float32, ctx)
+        peers = grp.share(color)
+        mode = e.abi.GATHER_ROOT if gather == "root" else e.abi.GATHER_ALL
+        for _ in range(3):  # repeated frames: the device barrier keeps the ranks in step
+            grp.render(e.BlendTris(), geom, peers, depth, gather=mode, clear=(0xFF000000, 1.0))
+        ctx.sync()
+        sync.wait()
+        frames[rank] = (color.raw().copy(), depth.raw().copy(), grp.rows(h))
+        sync.wait()
+        del peers, color, depth, geom
+
+    _two_ranks(run)
+    c0, _, _ = frames[0]
+    assert np.array_equal(c0, rpx), "root frame (this shader has no transcendental: bit-exact)"
+    for rank in (0, 1):
+        c, z, (r0, r1) = frames[rank]
+        assert_depth_bit_exact(z[r0:r1], rz[r0:r1], f"rank {rank} depth band")
+        if gather == "all" or rank == 0:
+            assert_colour_within_1lsb(c, rpx, f"rank {rank} gathered frame")
+        else:
+            assert_colour_within_1lsb(c[r0:r1], rpx[r0:r1], "rank 1 own band")
+            other = np.ones(h, bool); other[r0:r1] = False
+            assert (c[other] == 0x11111111).all(), "under the root gather a non-root rank receives nothing"
+
+
+def test_group_allgather_geom_completes_sharded_uploads():
+    w, h = 1024, 768
+    verts, idx = scenes.blend_tris(1 << 17, w, h, seed=9)   # 16 MB of vertices, 3 MB of indices
+    rpx, rz, _ = _oracle_frame(verts, w, h, idx)
+    out = {}
+
+    def run(rank, ctx, grp, sync):
+        geom = e.Geometry(np.zeros_like(verts), np.zeros_like(idx), ctx)   # same shape on every rank, nothing uploaded yet
+        (v0, v1), (i0, i1) = parallel.frame_shards(verts.shape[0], 2)[rank], parallel.frame_shards(idx.size, 2)[rank]
+        vs, is_ = np.ascontiguousarray(verts[v0:v1]), np.ascontiguousarray(idx[i0:i1])
+        geom.update_range(vs.ctypes.data, v0, v1 - v0, is_.ctypes.data, i0, i1 - i0)
+        grp.allgather_geom(geom)
+        color = e.Buffer2d([w, h], np.uint32, ctx)
+        depth = e.Buffer2d([w, h], np.float32, ctx)
+        e.BlendTris().render(geom, color, depth, clear=(0xFF000000, 1.0))
+        ctx.sync()
+        out[rank] = (color.raw().copy(), depth.raw().copy())
+        sync.wait()
+        del color, depth, geom
+
+    _two_ranks(run)
+    for rank in (0, 1):
+        assert_depth_bit_exact(out[rank][1], rz, f"rank {rank}")
+        assert_colour_within_1lsb(out[rank][0], rpx, f"rank {rank}")

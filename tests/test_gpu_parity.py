@@ -195,7 +195,7 @@ def test_textured_cube(frame, wrap, filt):
         return e.Cube(mvp, s)
 
     gpx, _, rpx, _, gs, rs = run_both(make, verts, w, h, clear_px=180, indices=idx, want_z=False, tex=tex)
-    assert np.array_equal(gpx != 180, rpx != 180) or True
+    assert np.array_equal(gpx != 180, rpx != 180), "coverage (texels are opaque: a covered pixel is never the clear value 180)"
     assert_colour_within_1lsb(gpx, rpx, "cube")
     assert gs["fragments"] == rs["fragments"] and rs["fragments"] > 100000
 

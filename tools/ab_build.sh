@@ -6,7 +6,7 @@ mkdir -p build/ab
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 -shared -Xcompiler -fPIC $flags \
-     -o build/ab/libeuc_$name.so euc_b200/csrc/euc_b200.cu -ldl &
+     -o build/ab/libeuc_$name.so euc_b200/csrc/euc_b200.cu -ldl -lrt &
 done
 wait
 ls -la build/ab
