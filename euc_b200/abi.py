@@ -26,7 +26,7 @@ HAND_LEFT, HAND_RIGHT = range(2)
 FILTER_NEAREST, FILTER_LINEAR = range(2)
 WRAP_NONE, WRAP_CLAMP, WRAP_TILE, WRAP_MIRROR = range(4)
 TEXEL_F32, TEXEL_RGBA8_TO_F32 = range(2)
-STAGE_NAMES = ("setup", "alloc", "fill", "resolve", "raster")
+STAGE_NAMES = ("setup", "alloc", "fill", "resolve", "raster", "classify")
 
 
 class SamplerDesc(C.Structure):

@@ -84,6 +84,9 @@ struct euc_ctx {
     bool stats = false;
     struct ClearReq { bool px = false, z = false; uint32_t px_value = 0, z_value = 0; } next_clear;  // euc_render_clear: consumed by the next render
     int sparse_recs = -1;  // EUC_SPARSE_RECS (development): -1 = automatic, 0 / 1 = force
+    // Smallest group whose ranks classify the primitives together (sort-middle of ids, group.inc) instead of each setting up
+    // the whole stream; 0 = never.  EUC_GROUP_CLS_MIN_WORLD overrides (tests use 2).
+    uint32_t group_cls_min_world = 0;
     euc_render_stats last{};
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
     int sm_count = 148;
@@ -93,7 +96,7 @@ struct euc_ctx {
     bool profiling = false;
     cudaEvent_t ev_counts = nullptr, ev_setup = nullptr;
     cudaStream_t aux = nullptr;  // counter read-back
-    struct BinHint { uint32_t cap = 128; bool verified = false; };  // cap 0 = use the exact path
+    struct BinHint { uint32_t cap = 128; bool verified = false; uint32_t n_tris = 0; };  // cap 0 = use the exact path; n_tris: primitives of the last checked render
     std::unordered_map<uint32_t, BinHint> bin_hint;       // per tile-count: bin size of the fast path
     std::vector<std::array<cudaEvent_t, 2>> pending[EUC_STAGE_COUNT];  // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool;
@@ -225,6 +228,7 @@ struct RenderCall {
     const euc_buf* mirrors = nullptr;
     uint32_t n_mirrors = 0;
     bool maybe_oob_sync = false;  // the host knows the index bounds and they do not prove every draw in range: checked render
+    bool group_cls = false;       // euc_group_render: the ranks classify 1/world of the primitives each and exchange ids (group.inc)
 };
 
 // What the render driver needs from a pipeline: sizes, flags, and how to launch its kernels on ctx->stream.
@@ -233,6 +237,7 @@ struct PipeOps {
     bool has_fragment = false, defer = false, needs_sampler = false, vec4_loads = false;
     int sampler_format = -1;
     std::function<void(const Params&, uint32_t blocks)> setup;
+    std::function<void(const Params&, uint32_t blocks)> group_classify;  // the same across a group (optional)
     std::function<void(const Params&, bool msaa, uint32_t blocks, uint32_t n_tiles)> raster;
     std::function<void(const Params&, bool msaa, uint32_t grid)> resolve;
     std::function<int(bool msaa)> resident;
@@ -269,6 +274,11 @@ struct DropClear {
     euc_ctx* ctx;
     ~DropClear() { if (ctx) ctx->next_clear = euc_ctx::ClearReq{}; }
 };
+
+// group.inc: fills the cls_* / surv_* fields of prm for a render whose primitives the group classifies together; launches
+// the group barrier that carries this rank's per-destination counts.
+int group_cls_prepare(euc_ctx* ctx, Params& prm);
+int group_cls_barrier(euc_ctx* ctx);
 
 // Pipeline-agnostic render driver.  `ops` describes the pipeline (record size, flags) and launches its kernels: template
 // instantiations for the built-in pipelines, NVRTC-compiled modules for pipelines registered at run time.
@@ -373,7 +383,10 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     }
     const uint32_t cap = hint.cap;
     const bool fast = cap > 0 && (size_t)n_tiles * cap * 4 <= ((size_t)1 << 30);
-    const bool go_async = fast && ctx->async && hint.verified && !rc.maybe_oob_sync;
+    // asynchronous only for a shape that a checked render has seen: same tile grid AND same primitive count (a frame loop over
+    // one scene); another scene on the same target is checked once first, so that an arbitrarily denser scene is sized by
+    // the exact path instead of overrunning the overflow buffer
+    const bool go_async = fast && ctx->async && hint.verified && hint.n_tris == prm.n_tris && !rc.maybe_oob_sync;
     if (capturing && !go_async)
         return fail(ctx, EUC_E_UNSUPPORTED, "this render needs a host check (first render of a target shape, or index bounds the host cannot prove): run it once outside stream capture");
     if (fast) {
@@ -394,8 +407,22 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
             prm.summary = ctx->summary_dev;
             prm.seq = ++ctx->seq;
         }
+        // a rank's band of a large frame: list the primitives that meet the band first (light kernel, full occupancy), set up those
+        // (inside a group the ranks share that work: each classifies 1/world of the primitives and sends the ids where they belong)
+        const bool gcls = rc.group_cls && ops.group_classify && prm.n_tris > (1u << 16);
+        if (gcls) {
+            if ((rcode = group_cls_prepare(ctx, prm)) != EUC_OK) return rcode;
+            prm.sparse_recs = 1;
+        }
         CU(cudaMemsetAsync(ctx->counters, 0, CTR_CLEAR_WORDS * sizeof(unsigned long long), ctx->stream));
-        { StageTimer t(ctx, EUC_STAGE_SETUP); ops.setup(prm, tri_blocks); }
+        if (gcls) {
+            CU(cudaMemsetAsync(prm.cls_counts, 0, EUC_MAX_GROUP * sizeof(uint32_t), ctx->stream));
+            { StageTimer t(ctx, EUC_STAGE_CLASSIFY); ops.group_classify(prm, (prm.cls_n + 255) / 256); }
+            if ((rcode = group_cls_barrier(ctx)) != EUC_OK) return rcode;
+        }
+        // list mode: a machine-sized grid strides over the list (its length is only known on the device)
+        const uint32_t setup_blocks = gcls ? std::min<uint32_t>(tri_blocks, (uint32_t)ctx->sm_count * 5u) : tri_blocks;
+        { StageTimer t(ctx, EUC_STAGE_SETUP); ops.setup(prm, setup_blocks); }
         if (go_async) {
             launch_raster();
             CU(cudaGetLastError());
@@ -420,6 +447,7 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
         }
         if (!(ctx->counters_host[3] & 2ull)) {
             hint.verified = true;  // this shape fits bins of `cap`: later renders run asynchronously
+            hint.n_tris = prm.n_tris;
             ctx->bin_hint[n_tiles] = hint;
             return EUC_OK;
         }
@@ -434,6 +462,8 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
     prm.bin_cap = 0;
     prm.ovf_cap = 0;
     prm.summary = nullptr;
+    prm.survivors = nullptr;
+    if (rc.group_cls) prm.sparse_recs = ctx->sparse_recs >= 0 ? (uint32_t)ctx->sparse_recs : ((uint64_t)(prm.row_end - prm.row_begin) * 2 < prm.h ? 1u : 0u);
     if ((rcode = ensure(ctx, ctx->tile_list, std::max<size_t>((size_t)prm.n_tris * 3, 1u << 16) * 4)) != EUC_OK) return rcode;
     prm.tile_list = (uint32_t*)ctx->tile_list.p;
     prm.list_capacity = (uint32_t)std::min<size_t>(ctx->tile_list.cap / 4, 0xfffffff0u);
@@ -469,6 +499,7 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
         const unsigned long long want = ((longest + longest / 4 + 32) + 31) / 32 * 32;
         hint.cap = (want * n_tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
         hint.verified = hint.cap != 0;
+        hint.n_tris = prm.n_tris;
         ctx->bin_hint[n_tiles] = hint;
     }
     if (ctx->counters_host[3] & 2ull) {
@@ -500,7 +531,12 @@ template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx, 
     ops.uniform_bytes = std::is_same<P, PipeBlendTris>::value ? 0u : (uint32_t)sizeof(typename P::Uniforms);
     ops.has_fragment = P::HAS_FRAGMENT; ops.defer = DEFER;
     ops.needs_sampler = PI::needs_sampler; ops.sampler_format = PI::sampler_format; ops.vec4_loads = PI::vec4_loads;
-    ops.setup = [ctx](const Params& prm, uint32_t blocks) { (LINES ? setup_lines_kernel<P> : setup_kernel<P>)<<<blocks, 128, 0, ctx->stream>>>(prm); };
+    ops.setup = [ctx](const Params& prm, uint32_t blocks) {
+        if (LINES) setup_lines_kernel<P><<<blocks, 128, 0, ctx->stream>>>(prm);
+        else if (prm.survivors) setup_kernel<P, true><<<blocks, 128, 0, ctx->stream>>>(prm);
+        else setup_kernel<P, false><<<blocks, 128, 0, ctx->stream>>>(prm);
+    };
+    if (!LINES) ops.group_classify = [ctx](const Params& prm, uint32_t blocks) { group_classify_kernel<P><<<blocks, 256, 0, ctx->stream>>>(prm); };
     ops.raster = [ctx](const Params& prm, bool msaa, uint32_t blocks, uint32_t n_tiles) {
         auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
         kern<<<blocks, RASTER_WARPS * 32, raster_smem_bytes<P, DEFER>(), ctx->stream>>>(prm, n_tiles);
@@ -812,6 +848,7 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
         cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EUC_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     if (const char* e = getenv("EUC_SPARSE_RECS")) ctx->sparse_recs = atoi(e);
+    if (const char* e = getenv("EUC_GROUP_CLS_MIN_WORLD")) ctx->group_cls_min_world = (uint32_t)std::max(atoi(e), 0);
     *out_ctx = ctx;
     return EUC_OK;
 }

@@ -96,6 +96,18 @@ struct Params {
     int32_t prim_kind;      // euc_primitive_kind
     uint32_t cta_bin;       // 1: primitives covering > 256 tiles are binned by the whole CTA (few, huge primitives)
     uint32_t sparse_recs;   // 1: live records are stored by their own lanes (row-restricted renders drop most primitives)
+    // Row-restricted renders of many primitives (a rank's band of a large frame): band_classify_kernel first lists the
+    // primitives whose vertical bounds meet the band (survivors[0 .. counters[9])), and the set-up kernel walks that list.
+    uint32_t* survivors;
+    // The list may come in slices, one per source rank of a group (group_classify_kernel): slice s holds surv_counts[s]
+    // ids from survivors + s * surv_stride on.  surv_counts == nullptr: one slice, its length in counters[9].
+    const uint32_t* surv_counts;
+    uint32_t surv_slices, surv_stride;
+    // Classification across a group (sort-middle of primitive ids): this rank looks at primitives [cls_first, cls_first +
+    // cls_n) of the frame and appends each to the list slice `cls_rank` of every rank whose band it meets (peer stores).
+    uint32_t* const* cls_lists;   // every rank's `survivors` base as mapped here
+    uint32_t* cls_counts;         // local fill of this rank's slice in each destination list
+    uint32_t cls_rank, cls_world, cls_band_rows, cls_first, cls_n;
     uint32_t bin_cap;       // > 0: fixed-capacity bins (tile t owns list[t*bin_cap ..]); setup appends directly, no alloc/fill pass
     // Bin overflow handled on the device (renders that never wait for the host): a pair that does not fit its tile's bin
     // goes to `ovf` (tile, primitive); the raster warp of such a tile collects its pairs into a slice of `ext`.
@@ -286,7 +298,7 @@ __device__ __forceinline__ void bin_big_warp(const Params& p, bool big, const Ti
             const uint32_t tx0 = __shfl_sync(full, r.tx0, j), ty0 = __shfl_sync(full, r.ty0, j), lb = __shfl_sync(full, r.layer_base, j);
             const uint32_t row = l / ntx, col = l - row * ntx;
             tl[k] = lb + (ty0 + row) * p.tiles_x + tx0 + col;
-            id[k] = tri - lane + j;  // lanes hold consecutive primitives
+            id[k] = __shfl_sync(full, tri, j);
             sl[k] = 0u;
             if (f < total) sl[k] = atomicAdd(p.tile_count + tl[k], 1u);
         }
@@ -349,11 +361,8 @@ constexpr uint32_t SETUP_LOCAL_TILES = 32;  // primitives covering up to this ma
 #ifndef EUC_SETUP_MIN_CTAS
 #define EUC_SETUP_MIN_CTAS 1
 #endif
-template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) setup_kernel(const __grid_constant__ Params p) {
+template <class P> __device__ __forceinline__ void setup_body(const Params& p, const uint32_t tri, const bool live, uint32_t (*rec_stage)[RecLayout<P>::WORDS]) {
     using L = RecLayout<P>;
-    __shared__ __align__(128) uint32_t rec_stage[128][L::WORDS];
-    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = tri < p.n_tris;
     uint2 bbox = make_uint2(0u, 0u);
     uint32_t layer = 0;
     bool oob = false;
@@ -440,7 +449,7 @@ template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) se
             // row-restricted renders (multi-GPU bands): primitives that miss this rank's rows are dropped here
             if (by1 <= p.row_begin || by0 >= p.row_end || bx1 <= bx0 || by1 <= by0) bbox = make_uint2(0u, 0u);
         }
-        p.tri_bbox[tri] = bbox;
+        if (!p.bin_cap) p.tri_bbox[tri] = bbox;  // read by the exact path's fill pass only
         valid = tile_rect(p, bbox, layer, r);
         nt = valid ? r.ntx * r.nty : 0u;
         if (p.bin_cap && valid && nt <= SETUP_LOCAL_TILES) {
@@ -588,6 +597,92 @@ template <class P> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) se
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
     if ((threadIdx.x & 31u) == 0 && npairs) atomicAdd(p.counters + 0, (unsigned long long)npairs);
+}
+
+template <class P, bool LIST = false> __global__ void __launch_bounds__(128, EUC_SETUP_MIN_CTAS) setup_kernel(const __grid_constant__ Params p) {
+    using L = RecLayout<P>;
+    __shared__ __align__(128) uint32_t rec_stage[128][L::WORDS];
+    if constexpr (!LIST) {  // one thread per primitive of the render
+        const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+        setup_body<P>(p, tri, tri < p.n_tris, rec_stage);
+        return;
+    }
+    // list mode (row bands): a machine-sized grid strides over the (sliced) list of primitives that meet this rank's rows;
+    // the host does not know its length, and a grid sized for all primitives would spend its time launching empty CTAs
+    uint32_t pre[EUC_MAX_GROUP + 1];
+    pre[0] = 0;
+    if (p.surv_counts) {
+#pragma unroll
+        for (uint32_t k = 0; k < EUC_MAX_GROUP; ++k) pre[k + 1] = pre[k] + (k < p.surv_slices ? *(volatile const uint32_t*)(p.surv_counts + k) : 0u);
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < EUC_MAX_GROUP; ++k) pre[k + 1] = (uint32_t)*(volatile unsigned long long*)(p.counters + 9);
+    }
+    const uint32_t total = pre[EUC_MAX_GROUP];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool live = i < total;
+        uint32_t tri = 0;
+        if (live) {
+            uint32_t sl = 0, start = 0;
+#pragma unroll
+            for (uint32_t k = 1; k < EUC_MAX_GROUP; ++k) if (p.surv_counts && i >= pre[k]) { sl = k; start = pre[k]; }
+            tri = p.survivors[(size_t)sl * p.surv_stride + (i - start)];
+        }
+        setup_body<P>(p, tri, live, rec_stage);
+    }
+}
+
+// Group pre-pass: like band_classify_kernel, but this rank looks at its share of the frame's primitives only and routes
+// each to the rank(s) whose row band it meets, by appending the id to its own slice of that rank's list (peer store).
+// Slices cannot overflow: a slice holds at most this rank's share.  The fills travel with the group barrier that follows.
+template <class P> __global__ void __launch_bounds__(256) group_classify_kernel(const __grid_constant__ Params p) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t r_lo = 1, r_hi = 0;  // destination ranks [r_lo, r_hi]
+    const uint32_t tri = p.cls_first + k;
+    if (k < p.cls_n) {
+        const uint32_t d = find_draw(p, tri);
+        const DrawDev dr = draw_of(p, d);
+        const typename P::Uniforms& u = uniforms_of<P>(p, d);
+        const uint32_t s0 = dr.first + 3u * (tri - dr.tri_begin);
+        float sy[3];
+        bool oob = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            long long vi = p.indices ? (long long)__ldg(p.indices + s0 + i) + dr.base_vertex : (long long)(s0 + i) + dr.base_vertex;
+            if (vi < 0 || vi >= (long long)p.n_vertices) { oob = true; vi = 0; }
+            float4 clip;
+            float var[P::V > 0 ? P::V : 1];
+            P::vertex(u, p.vertices + (size_t)vi * p.vstride, clip, var);
+            const float hy = clip.y * p.flip_y;
+            sy[i] = (float)p.h * ((hy / clip.w) * -0.5f + 0.5f);
+        }
+        const uint32_t eby0 = r_as_usize_clamped(r_min(r_min(sy[0], sy[1]), sy[2]) + 0.0f, 0u, p.h);
+        const uint32_t eby1 = r_as_usize_clamped(r_max(r_max(sy[0], sy[1]), sy[2]) + 1.0f, 0u, p.h);
+        if (oob) { r_lo = 0; r_hi = p.cls_world - 1u; }  // every rank's set-up kernel sees (and reports) the bad index
+        else if (eby1 > eby0) { r_lo = eby0 / p.cls_band_rows; r_hi = min((eby1 - 1u) / p.cls_band_rows, p.cls_world - 1u); }
+    }
+    // One global atomic per CTA and destination (same-address atomics serialise in L2: one per warp already cost more
+    // than everything else here): warps take their offsets from shared-memory counters, the CTA takes one range per
+    // destination, and the lanes bound for rank r write consecutive slots.
+    __shared__ uint32_t cta_cnt[EUC_MAX_GROUP], cta_base[EUC_MAX_GROUP];
+    const uint32_t lane = threadIdx.x & 31u;
+    if (threadIdx.x < EUC_MAX_GROUP) cta_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t woff[EUC_MAX_GROUP];
+#pragma unroll
+    for (uint32_t r = 0; r < EUC_MAX_GROUP; ++r) {
+        const uint32_t m = __ballot_sync(0xffffffffu, r_lo <= r && r <= r_hi);
+        uint32_t o = 0;
+        if (m && lane == 0) o = atomicAdd(&cta_cnt[r], (uint32_t)__popc(m));
+        woff[r] = __shfl_sync(0xffffffffu, o, 0) + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x < EUC_MAX_GROUP) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(p.cls_counts + threadIdx.x, cta_cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < EUC_MAX_GROUP; ++r)
+        if (r_lo <= r && r <= r_hi) p.cls_lists[r][(size_t)p.cls_rank * p.surv_stride + cta_base[r] + woff[r]] = tri;
 }
 
 // -------------------------------------------------------------------------------------------------------

@@ -201,7 +201,7 @@ uint64_t euc_blocking_waits(euc_ctx* ctx);
 int euc_set_stats(euc_ctx* ctx, int enabled);
 int euc_get_stats(euc_ctx* ctx, euc_render_stats* out); /* blocking; stats of the last render call */
 /* Per-stage device timing (CUDA events on the context's stream around every kernel of a render call). */
-enum euc_stage { EUC_STAGE_SETUP = 0, EUC_STAGE_ALLOC = 1, EUC_STAGE_FILL = 2, EUC_STAGE_RESOLVE = 3, EUC_STAGE_RASTER = 4, EUC_STAGE_COUNT = 5 };
+enum euc_stage { EUC_STAGE_SETUP = 0, EUC_STAGE_ALLOC = 1, EUC_STAGE_FILL = 2, EUC_STAGE_RESOLVE = 3, EUC_STAGE_RASTER = 4, EUC_STAGE_CLASSIFY = 5, EUC_STAGE_COUNT = 6 };
 int euc_set_profiling(euc_ctx* ctx, int enabled);
 /* Blocking. ms[EUC_STAGE_COUNT] = accumulated milliseconds per stage since the last reset; calls[] = launches per stage. */
 int euc_get_profile(euc_ctx* ctx, float* ms, uint64_t* calls, int reset);

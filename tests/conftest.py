@@ -4,6 +4,11 @@ import sys
 import numpy as np
 import pytest
 
+# Two tests run two ranks of a multi-GPU group as two host threads on ONE GPU.  With CUDA's default lazy module loading the
+# first launch of a kernel synchronises the device, which would wait for the other rank's barrier kernel (spinning until this
+# rank arrives): load every kernel up front.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

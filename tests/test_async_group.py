@@ -35,28 +35,49 @@ def _oracle_frame(verts, w, h, idx=None):
     return rpx, rz, st
 
 
+def _spread_tris(n, seed):
+    """n small triangles spread over the whole target (short tile lists)."""
+    r = scenes.u01(seed, n * 3 * 8).reshape(n, 3, 8)
+    v = np.zeros((n, 3), dtype=e.VERTEX_P4C4)
+    cx, cy = r[:, 0, 6] * 1.9 - 0.95, r[:, 0, 7] * 1.9 - 0.95
+    v["pos"][:, :, 0] = cx[:, None] + (r[:, :, 0] - 0.5) * 0.02
+    v["pos"][:, :, 1] = cy[:, None] + (r[:, :, 1] - 0.5) * 0.2
+    v["pos"][:, :, 2] = r[:, :, 2]
+    v["pos"][:, :, 3] = 1.0
+    v["rgba"][:, :, :3] = r[:, :, 3:6]
+    v["rgba"][:, :, 3] = 0.5
+    return v.reshape(-1)
+
+
 def test_bin_overflow_is_handled_on_the_device_without_a_host_wait():
     ctx = e.Context(0)
     w, h = 640, 64
     px = e.Buffer2d([w, h], np.uint32, ctx)
     z = e.Buffer2d([w, h], np.float32, ctx)
     pipe = e.BlendTris()
-    # first render of this target shape: checked (the host waits for set-up), lists far below the 128-slot bins
-    pipe.render(_stacked_tris(40, 1), px, z, clear=(0xFF000000, 1.0))
+    n = 3000
+    # first render of this shape (target size, primitive count): checked; its lists stay far below the 128-slot bins
+    pipe.render(_spread_tris(n, 1), px, z, clear=(0xFF000000, 1.0))
     ctx.sync()
     waits = ctx.blocking_waits()
     assert waits >= 1
-    for n in (700, 3000, 700):  # lists of ~n entries per tile: 128-slot bins overflow, the device collects the rest
-        v = _stacked_tris(n, 1234 + n)
+    for k in range(3):  # same shape, all primitives on a few tiles: lists of ~n entries, the bins overflow, the device collects the rest
+        v = _stacked_tris(n, 1234 + k)
         ctx.set_stats(True)
         pipe.render(v, px, z, clear=(0xFF000000, 1.0))
         st = ctx.get_stats()
         ctx.set_stats(False)
         rpx, rz, rs = _oracle_frame(v, w, h)
         assert st["fragments"] == rs["fragments"]
-        assert_depth_bit_exact(z.raw(), rz, f"overflow n={n}")
-        assert_colour_within_1lsb(px.raw(), rpx, f"overflow n={n}")
+        assert_depth_bit_exact(z.raw(), rz, f"overflow pass {k}")
+        assert_colour_within_1lsb(px.raw(), rpx, f"overflow pass {k}")
     assert ctx.blocking_waits() == waits, "asynchronous renders must not wait for the device"
+    # another primitive count on the same target: checked once (the exact path sizes it), correct as well
+    v = _stacked_tris(700, 5)
+    pipe.render(v, px, z, clear=(0xFF000000, 1.0))
+    rpx, rz, _ = _oracle_frame(v, w, h)
+    assert_depth_bit_exact(z.raw(), rz, "other scene")
+    assert ctx.blocking_waits() > waits
     del px, z
     ctx.close()
 
@@ -145,6 +166,7 @@ def test_whole_frame_replays_from_a_cuda_graph():
 
 def _two_ranks(fn):
     """Runs fn(rank, ctx, group, sync) on two host threads, one context each on GPU 0; re-raises the first failure."""
+    os.environ["EUC_GROUP_CLS_MIN_WORLD"] = "2"   # exercise the shared classification of primitives with two ranks
     name = f"t{os.getpid()}_{np.random.randint(1 << 30)}"
     errs, host_barrier = [], threading.Barrier(2)
 
@@ -167,13 +189,14 @@ def _two_ranks(fn):
     for t in ts:
         t.join(timeout=300)
     if errs:
-        raise errs[0]
+        raise AssertionError(" | ".join(f"{type(x).__name__}: {x}" for x in errs)) from errs[0]
 
 
-@pytest.mark.parametrize("gather", ["root", "all"])
-def test_group_render_gathers_row_bands(gather):
+@pytest.mark.parametrize("gather,n_quads", [("root", 1 << 13), ("all", 1 << 13), ("root", 1 << 16), ("all", 3 << 15)])
+def test_group_render_gathers_row_bands(gather, n_quads):
+    """n_quads > 2^15 (more than 65536 primitives): the ranks classify half of the primitives each and exchange the ids."""
     w, h = 1024, 768
-    verts, idx = scenes.blend_tris(1 << 13, w, h, seed=3, size_px=(3.0, 20.0))
+    verts, idx = scenes.blend_tris(n_quads, w, h, seed=3, size_px=(3.0, 20.0) if n_quads < (1 << 15) else (2.0, 7.0))
     rpx, rz, _ = _oracle_frame(verts, w, h, idx)
     frames = {}
 
@@ -183,6 +206,13 @@ def test_group_render_gathers_row_bands(gather):
         depth = e.Buffer2d([w, h], np.float32, ctx)
         peers = grp.share(color)
         mode = e.abi.GATHER_ROOT if gather == "root" else e.abi.GATHER_ALL
+        # Both ranks of this test share ONE GPU: a device-wide synchronising call (cudaMalloc / cudaFree of a scratch buffer) on
+        # one thread would wait for the other rank's barrier kernel, which spins until this rank arrives.  One plain render
+        # sizes the scratch buffers first.  (With one GPU per rank - the real configuration - the situation cannot arise.)
+        e.BlendTris().render(geom, color, depth, clear=(0xFF000000, 1.0))
+        color.clear(0x11111111)
+        ctx.sync()
+        sync.wait()
         for _ in range(3):  # repeated frames: the device barrier keeps the ranks in step
             grp.render(e.BlendTris(), geom, peers, depth, gather=mode, clear=(0xFF000000, 1.0))
         ctx.sync()
