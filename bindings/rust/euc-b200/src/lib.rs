@@ -109,3 +109,80 @@ where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasteri
     ctx.check(unsafe { sys::euc_render(ctx.raw, &d, vertices.as_ptr() as *const _, 24, vertices.len() as u32,
                                        std::ptr::null(), 0, color.handle, depth.handle) })
 }
+
+/// `IndexedVertices::new(indices, verts)` for vertices of 32 bytes (euc_vertex_p4uv / euc_vertex_p4c4 / euc_vertex_voxel)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct Vertex32 { pub words: [f32; 8] }
+
+fn indexed_render<'r, P: euc::Pipeline<'r>>(ctx: &Context, d: &sys::euc_pipeline_desc, indices: &[u32], vertices: &[Vertex32],
+                                             color: sys::euc_buf, depth: sys::euc_buf) -> Result<(), Error> {
+    ctx.check(unsafe { sys::euc_render(ctx.raw, d, vertices.as_ptr() as *const _, 32, vertices.len() as u32, indices.as_ptr(), indices.len() as u32, color, depth) })
+}
+
+/// `Cube { mvp, sampler }.render(IndexedVertices::new(INDICES, VERTICES), &mut color, &mut Empty::default())`
+/// (examples/texture_mapping.rs:5-35, :146-151).  `texture`: RGBA8 texels uploaded as a `Buffer2d<u32>`; `wrap`: EUC_WRAP_*.
+pub fn render_cube<'r, P: euc::Pipeline<'r>>(ctx: &Context, pipe: &P, mvp: vek::Mat4<f32>, texture: &Buffer2d<u32>, filter: i32, wrap: i32,
+                                            indices: &[u32], vertices: &[Vertex32], color: &mut Buffer2d<u32>) -> Result<(), Error>
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    let u = mvp.into_col_array();
+    let mut d = desc_of(pipe, sys::EUC_PIPE_TEX_CUBE, &u);
+    d.samplers[0] = sys::euc_sampler_desc { buf: texture.handle, format: sys::EUC_TEXEL_RGBA8_TO_F32, filter, wrap, _pad: 0 };
+    indexed_render::<P>(ctx, &d, indices, vertices, color.handle, 0 /* euc::Empty */)
+}
+
+/// BASELINE config 4: pre-transformed rgba triangles, depth test + src-over blend (pipeline id EUC_PIPE_BLEND_TRIS).
+pub fn render_blend_tris<'r, P: euc::Pipeline<'r>>(ctx: &Context, pipe: &P, indices: &[u32], vertices: &[Vertex32],
+                                                  color: &mut Buffer2d<u32>, depth: &mut Buffer2d<f32>) -> Result<(), Error>
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    let d = desc_of(pipe, sys::EUC_PIPE_BLEND_TRIS, &[]);
+    indexed_render::<P>(ctx, &d, indices, vertices, color.handle, depth.handle)
+}
+
+/// Device-resident geometry (`euc_geom_create`): the vertex slice + `IndexedVertices` of a frame loop that renders it many times.
+pub struct Geometry<'c> { ctx: &'c Context, handle: sys::euc_geom }
+impl<'c> Geometry<'c> {
+    pub fn new(ctx: &'c Context, vertices: &[Vertex32], indices: &[u32]) -> Result<Self, Error> {
+        let mut handle = 0;
+        ctx.check(unsafe { sys::euc_geom_create(ctx.raw, vertices.as_ptr() as *const _, 32, vertices.len() as u32, indices.as_ptr(), indices.len() as u32, &mut handle) })?;
+        Ok(Self { ctx, handle })
+    }
+}
+impl Drop for Geometry<'_> { fn drop(&mut self) { unsafe { sys::euc_geom_destroy(self.ctx.raw, self.handle); } } }
+
+/// BASELINE config 5: `draws.len()` independent `VoxelIcon { mvp, light_dir }.render(..)` calls, icon i into layer `draws[i].layer`
+/// of the layered targets, in one launch sequence.  `uniforms`: 20 floats per icon (mvp column-major, light_dir.xyz_).
+pub fn render_voxel_batch<'r, P: euc::Pipeline<'r>>(ctx: &Context, pipe: &P, geom: &Geometry, draws: &[sys::euc_batch_draw], uniforms: &[[f32; 20]],
+                                                   color: sys::euc_buf, depth: sys::euc_buf) -> Result<(), Error>
+where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+    assert_eq!(draws.len(), uniforms.len());
+    let mut d = desc_of(pipe, sys::EUC_PIPE_VOXEL_ICON, &[]);
+    d.uniform_bytes = 80;
+    ctx.check(unsafe { sys::euc_render_batch(ctx.raw, &d, geom.handle, draws.as_ptr(), draws.len() as u32, uniforms.as_ptr() as *const _, color, depth) })
+}
+
+/// One rank of a multi-GPU job on one node (one process or thread per GPU): what `render_par`'s thread pool over row bands
+/// (src/pipeline.rs:304-366) becomes with a GPU per band.  Collective calls must be made by every rank in the same order.
+pub struct Group<'c> { ctx: &'c Context, pub rank: u32, pub world: u32 }
+impl<'c> Group<'c> {
+    pub fn join(ctx: &'c Context, name: &str, rank: u32, world: u32) -> Result<Self, Error> {
+        let c = std::ffi::CString::new(name).unwrap();
+        ctx.check(unsafe { sys::euc_group_create(ctx.raw, c.as_ptr(), rank, world) })?;
+        Ok(Self { ctx, rank, world })
+    }
+    /// Every rank passes its colour target; returns all ranks' targets as mapped into this context (NVLink peer memory).
+    pub fn share(&self, color: &Buffer2d<u32>) -> Result<Vec<sys::euc_buf>, Error> {
+        let mut peers = vec![0u64; self.world as usize];
+        self.ctx.check(unsafe { sys::euc_group_share_buf(self.ctx.raw, color.handle, peers.as_mut_ptr()) })?;
+        Ok(peers)
+    }
+    /// This rank's row band of the frame; the band's colour rows also land in rank 0's target (`gather_all`: in every rank's).
+    pub fn render_blend_tris<'r, P: euc::Pipeline<'r>>(&self, pipe: &P, geom: &Geometry, peers: &[sys::euc_buf], depth: &mut Buffer2d<f32>, gather_all: bool) -> Result<(), Error>
+    where <<P::Primitives as euc::primitives::PrimitiveKind<P::VertexData>>::Rasterizer as euc::rasterizer::Rasterizer>::Config: Into<euc::CullMode> {
+        let d = desc_of(pipe, sys::EUC_PIPE_BLEND_TRIS, &[]);
+        let mode = if gather_all { sys::EUC_GATHER_ALL } else { sys::EUC_GATHER_ROOT };
+        self.ctx.check(unsafe { sys::euc_group_render(self.ctx.raw, &d, geom.handle, peers.as_ptr(), depth.handle, mode) })
+    }
+    pub fn barrier(&self) -> Result<(), Error> { self.ctx.check(unsafe { sys::euc_group_barrier(self.ctx.raw) }) }
+}
+impl Drop for Group<'_> { fn drop(&mut self) { unsafe { sys::euc_group_destroy(self.ctx.raw); } } }

@@ -87,6 +87,7 @@ struct euc_ctx {
     // Smallest group whose ranks classify the primitives together (sort-middle of ids, group.inc) instead of each setting up
     // the whole stream; 0 = never.  EUC_GROUP_CLS_MIN_WORLD overrides (tests use 2).
     uint32_t group_cls_min_world = 0;
+    uint64_t ovf_fixed = 0;  // EUC_OVF_ENTRIES (tests): fixed size of the bin-overflow buffer instead of the adaptive one
     euc_render_stats last{};
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
     int sm_count = 148;
@@ -145,9 +146,10 @@ void poll_summary(euc_ctx* ctx) {
         if (want > it->second.cap) it->second.cap = (want * tiles * 4 <= (1ull << 30)) ? (uint32_t)want : 0u;
     }
     if (ovf * 2 > ctx->ovf_want) ctx->ovf_want = ovf * 2;
-    if ((flags & 5ull) && ctx->deferred_code == EUC_OK) {
-        if (flags & 1ull) { ctx->deferred_code = EUC_E_OUT_OF_BOUNDS; ctx->deferred_msg = "vertex index out of range in an earlier asynchronous render (that render drew nothing)"; }
-        else { ctx->deferred_code = EUC_E_OOM; ctx->deferred_msg = "an earlier asynchronous render overflowed its bin-overflow buffer and drew nothing; the buffer has been enlarged, re-issue the frame"; }
+    if (flags) {
+        // bit 2 (overflow buffer exhausted) needs no report: the affected tiles were rendered by scanning all primitives, and
+        // the buffer is larger from now on
+        if ((flags & 1ull) && ctx->deferred_code == EUC_OK) { ctx->deferred_code = EUC_E_OUT_OF_BOUNDS; ctx->deferred_msg = "vertex index out of range in an earlier asynchronous render (that render drew nothing)"; }
         cudaMemsetAsync(ctx->counters + 15, 0, sizeof(unsigned long long), ctx->stream);
     }
 }
@@ -396,7 +398,7 @@ int render_driver(euc_ctx* ctx, const RenderCall& rc, Params& prm, uint32_t n_ti
         prm.bin_cap = cap;
         if (ctx->async) {
             // sized on the checked render already: the asynchronous renders that follow (possibly inside stream capture) find them
-            const uint64_t want = std::max<uint64_t>({(uint64_t)1 << 18, (uint64_t)prm.n_tris * 2, ctx->ovf_want});
+            const uint64_t want = ctx->ovf_fixed ? ctx->ovf_fixed : std::max<uint64_t>({(uint64_t)1 << 18, (uint64_t)prm.n_tris * 2, ctx->ovf_want});
             if ((rcode = ensure(ctx, ctx->ovf, (size_t)want * sizeof(uint2))) != EUC_OK) return rcode;
             if ((rcode = ensure(ctx, ctx->ext, (size_t)want * 4)) != EUC_OK) return rcode;
         }
@@ -612,13 +614,10 @@ int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
     if (d.pipeline_id >= EUC_PIPE_USER_BASE) {
         if (ctx->user) { auto it = ctx->user->pipes.find(d.pipeline_id); if (it != ctx->user->pipes.end()) user_pipe = it->second; }
         if (!user_pipe) return fail(ctx, EUC_E_INVALID, "unknown run-time pipeline id %d", d.pipeline_id);
-        if (d.primitive_kind != EUC_PRIM_TRIANGLE_LIST) return fail(ctx, EUC_E_UNSUPPORTED, "run-time pipelines support TriangleList only");
     } else
     if (d.pipeline_id < 0 || d.pipeline_id >= EUC_PIPE_COUNT) return fail(ctx, EUC_E_INVALID, "unknown pipeline_id %d", d.pipeline_id);
     if (d.primitive_kind < 0 || d.primitive_kind > EUC_PRIM_LINE_TRIANGLE_LIST) return fail(ctx, EUC_E_INVALID, "unknown primitive kind %d", d.primitive_kind);
-    const bool lines = d.primitive_kind != EUC_PRIM_TRIANGLE_LIST;
-    if (lines && d.pipeline_id != EUC_PIPE_VERTEX_COLOR && d.pipeline_id != EUC_PIPE_WIREFRAME)
-        return fail(ctx, EUC_E_UNSUPPORTED, "line primitives are built for the VERTEX_COLOR and WIREFRAME pipelines only");
+    const bool lines = d.primitive_kind != EUC_PRIM_TRIANGLE_LIST;  // every pipeline renders lines too (primitives.rs:49-104 is generic over the pipeline)
     if (d.cull_mode < 0 || d.cull_mode > 2 || d.depth_test < 0 || d.depth_test > 3) return fail(ctx, EUC_E_INVALID, "bad cull/depth mode");
 
     const bool shadow = d.pipeline_id == EUC_PIPE_TEAPOT_SHADOW;
@@ -800,17 +799,19 @@ int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
     prm.tile_count = (uint32_t*)ctx->tile_count.p;
     prm.tile_range = (uint2*)ctx->tile_range.p;
 
-    if (user_pipe) return render_driver(ctx, rc, prm, n_tiles, user_pipe->ops);
+    if (user_pipe) return render_driver(ctx, rc, prm, n_tiles, lines ? user_pipe->ops_lines : user_pipe->ops);
+#define EUC_DISPATCH(P) rcode = lines ? render_typed<P, true>(ctx, rc, prm, n_tiles) : render_typed<P>(ctx, rc, prm, n_tiles); break
     switch (d.pipeline_id) {
-        case EUC_PIPE_TEAPOT_SHADOW: rcode = render_typed<PipeTeapotShadow>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_TEAPOT_PHONG: rcode = render_typed<PipeTeapotPhong>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_TEX_CUBE: rcode = render_typed<PipeTexCube>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_BLEND_TRIS: rcode = render_typed<PipeBlendTris>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_VOXEL_ICON: rcode = render_typed<PipeVoxelIcon>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_VERTEX_COLOR: rcode = lines ? render_typed<PipeVertexColor, true>(ctx, rc, prm, n_tiles) : render_typed<PipeVertexColor>(ctx, rc, prm, n_tiles); break;
-        case EUC_PIPE_WIREFRAME: rcode = lines ? render_typed<PipeWireframe, true>(ctx, rc, prm, n_tiles) : render_typed<PipeWireframe>(ctx, rc, prm, n_tiles); break;
+        case EUC_PIPE_TEAPOT_SHADOW: EUC_DISPATCH(PipeTeapotShadow);
+        case EUC_PIPE_TEAPOT_PHONG: EUC_DISPATCH(PipeTeapotPhong);
+        case EUC_PIPE_TEX_CUBE: EUC_DISPATCH(PipeTexCube);
+        case EUC_PIPE_BLEND_TRIS: EUC_DISPATCH(PipeBlendTris);
+        case EUC_PIPE_VOXEL_ICON: EUC_DISPATCH(PipeVoxelIcon);
+        case EUC_PIPE_VERTEX_COLOR: EUC_DISPATCH(PipeVertexColor);
+        case EUC_PIPE_WIREFRAME: EUC_DISPATCH(PipeWireframe);
         default: rcode = EUC_E_INVALID;
     }
+#undef EUC_DISPATCH
     // dd is pageable: make sure the async copy consumed it (render_typed synchronises; early outs do not)
     return rcode;
 }
@@ -849,6 +850,7 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     if (const char* e = getenv("EUC_SPARSE_RECS")) ctx->sparse_recs = atoi(e);
     if (const char* e = getenv("EUC_GROUP_CLS_MIN_WORLD")) ctx->group_cls_min_world = (uint32_t)std::max(atoi(e), 0);
+    if (const char* e = getenv("EUC_OVF_ENTRIES")) ctx->ovf_fixed = (uint64_t)std::max(atoll(e), 0ll);
     *out_ctx = ctx;
     return EUC_OK;
 }

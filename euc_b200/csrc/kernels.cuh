@@ -154,7 +154,8 @@ struct TileRect { uint32_t tx0, ty0, ntx, nty, layer_base; };
 // Error / abort flags of a render (counters[3])
 constexpr unsigned long long FLAG_OOB = 1ull;       // a vertex index was out of range
 constexpr unsigned long long FLAG_BINS = 2ull;      // a bin (or the pair list of the exact path) was too small: the host redoes the render
-constexpr unsigned long long FLAG_OVF_FULL = 4ull;  // the overflow buffer itself was too small: the render is dropped
+constexpr unsigned long long FLAG_OVF_FULL = 4ull;  // (informative) the overflow buffer was too small: some tiles were rendered by scanning all primitives
+constexpr uint32_t TILE_LOST = 0x80000000u;         // tile_count bit: pairs of this tile were dropped, its list is incomplete
 
 // Fast-path append of (tile <- primitive) when slot `sl` of the tile's bin has been taken.
 __device__ __forceinline__ void bin_store(const Params& p, uint32_t tile, uint32_t sl, uint32_t tri, bool& over) {
@@ -162,7 +163,15 @@ __device__ __forceinline__ void bin_store(const Params& p, uint32_t tile, uint32
         p.tile_list[(size_t)tile * p.bin_cap + sl] = tri;
     } else if (p.ovf_cap) {
         const unsigned long long k = atomicAdd(p.counters + 5, 1ull);
-        if (k < (unsigned long long)p.ovf_cap) p.ovf[k] = make_uint2(tile, tri); else over = true;
+        if (k < (unsigned long long)p.ovf_cap) {
+            p.ovf[k] = make_uint2(tile, tri);
+        } else {
+            // Not even the overflow buffer has room (a scene far denser than the ones this target has seen).  The pair is
+            // dropped and the tile marked: its raster warp ignores the lists and tests every primitive of the render against
+            // the tile instead (slow, but right, and nobody has to wait for the host).
+            atomicOr(p.tile_count + tile, TILE_LOST);
+            over = true;
+        }
     } else {
         over = true;
     }
@@ -449,7 +458,7 @@ template <class P> __device__ __forceinline__ void setup_body(const Params& p, c
             // row-restricted renders (multi-GPU bands): primitives that miss this rank's rows are dropped here
             if (by1 <= p.row_begin || by0 >= p.row_end || bx1 <= bx0 || by1 <= by0) bbox = make_uint2(0u, 0u);
         }
-        if (!p.bin_cap) p.tri_bbox[tri] = bbox;  // read by the exact path's fill pass only
+        p.tri_bbox[tri] = bbox;  // read by the exact path's fill pass and by raster warps that scan all primitives (TILE_LOST)
         valid = tile_rect(p, bbox, layer, r);
         nt = valid ? r.ntx * r.nty : 0u;
         if (p.bin_cap && valid && nt <= SETUP_LOCAL_TILES) {
@@ -833,7 +842,7 @@ __global__ void __launch_bounds__(256) alloc_tiles_kernel(const __grid_constant_
 
 // Non-zero when this render must not proceed: a vertex index was out of range (bit 0) or the pair list is too small
 // (bit 1).  Written before fill/raster start (stream order); the host re-launches them after growing the list.
-__device__ __forceinline__ bool render_aborted(const Params& p) { return (*(volatile unsigned long long*)(p.counters + 3) & (FLAG_OOB | FLAG_BINS | FLAG_OVF_FULL)) != 0ull; }
+__device__ __forceinline__ bool render_aborted(const Params& p) { return (*(volatile unsigned long long*)(p.counters + 3) & (FLAG_OOB | FLAG_BINS)) != 0ull; }
 
 __global__ void __launch_bounds__(128) fill_kernel(const __grid_constant__ Params p) {
     if (render_aborted(p)) return;
@@ -1167,9 +1176,9 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
 // One 16x16 tile, walked by one warp.
 // Not inlined on purpose: inside the persistent loop the register allocation of the (large) tile body got worse.
 // Returns (mbarrier phase after the tile, fragments emitted).
-template <class P, bool MSAA, bool DEFER, bool LINES>
+template <class P, bool MSAA, bool DEFER, bool LINES, bool SCAN>
 __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
-                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, uint32_t& max_list) {
+                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, uint32_t& max_list, const uint32_t cnt_raw) {
     using L = RecLayout<P>;
     uint32_t nfrag = 0;
     constexpr uint32_t SW = StageGeom<P, DEFER>::REC_WORDS;
@@ -1177,11 +1186,14 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
     uint2 rg;
     uint32_t n_bin;  // entries of the list that live in the tile's own bin / slice; the rest (bin overflow) in `ext`
+    // SCAN: the tile's list is incomplete (TILE_LOST): every primitive of the render is tested against the tile.  A separate
+    // instantiation, so that the ordinary tile loop carries none of its state.
+    constexpr bool scan_all = SCAN;
     if (p.bin_cap) {
-        const uint32_t cnt_t = p.tile_count[tile];
-        rg = make_uint2(tile * p.bin_cap, cnt_t);
+        const uint32_t cnt_t = cnt_raw & ~TILE_LOST;  // cnt_raw: tile_count[tile], read by the caller
+        rg = make_uint2(tile * p.bin_cap, scan_all ? 1u : cnt_t);
         __syncwarp();
-        if (lane == 0 && cnt_t) p.tile_count[tile] = 0u;  // leave the counters zeroed for the next render
+        if (lane == 0 && cnt_raw) p.tile_count[tile] = 0u;  // leave the counters zeroed for the next render
         n_bin = min(cnt_t, p.bin_cap);
     } else {
         rg = p.tile_range[tile];
@@ -1242,7 +1254,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     const bool short_list = n <= (uint32_t)IDS_REGS;
     uint32_t* const bin = p.tile_list + rg.x;
     uint32_t* ext = nullptr;
-    if (n > n_bin) {
+    if (!scan_all && n > n_bin) {
         // The bin overflowed (warp-uniform, rare: the host sizes the bins from the lists of earlier renders).  The pairs
         // that did not fit are somewhere in the overflow buffer: take a slice of `ext` and collect this tile's pairs.
         uint32_t base_e = 0;
@@ -1262,7 +1274,9 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     }
     auto lst = [&](uint32_t i) -> uint32_t& { return i < n_bin ? bin[i] : ext[i - n_bin]; };
     uint32_t v[4];
-    if (short_list) {
+    if (scan_all) {
+        v[0] = v[1] = v[2] = v[3] = 0u;  // ids come from the scan below, already in submission order
+    } else if (short_list) {
 #pragma unroll
         for (uint32_t r = 0; r < 4; ++r) v[r] = r * 32 + lane < n ? lst(r * 32 + lane) : 0xffffffffu;
         if (n > 1) bitonic_regs128(v, lane);
@@ -1364,12 +1378,45 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     // primitives of the round.  Longer rounds bring the busiest lane closer to the mean (the round ends when the last
     // lane is done); the load of the next round is hidden by the other warps of the SM.
     constexpr uint32_t ROUND = NB * BATCH;
-    const uint32_t n_rounds = (n + ROUND - 1) / ROUND;
+    const uint32_t n_rounds = scan_all ? 0xffffffffu : (n + ROUND - 1) / ROUND;
+    uint32_t scan_pos = 0;  // scan mode: next primitive id to test
     for (uint32_t rd = 0; rd < n_rounds; ++rd) {
         __syncwarp();  // every lane is done with the records of the previous round
-        const uint32_t cnt = min(ROUND, n - rd * ROUND);
+        uint32_t cnt, id0, id1 = 0u;
+        if (!scan_all) {
+            cnt = min(ROUND, n - rd * ROUND);
+            id0 = batch_id(NB * rd);
+            if (cnt > (uint32_t)BATCH) id1 = batch_id(NB * rd + 1u);
+        } else {
+            // Scan mode: collect the next (up to) 32 primitives whose bounds meet this tile's rows and columns, in id order.
+            // Lane t of the round must hold the t-th hit: hits of a group of 32 candidates are picked with find-nth-set.
+            cnt = 0u; id0 = 0u;
+            const uint32_t tpl = p.tiles_x * p.tiles_y, lay = tile / tpl, tl0 = tile - lay * tpl;
+            const uint32_t sty = (tl0 / p.tiles_x) * TILE, stx = (tl0 % p.tiles_x) * TILE;
+            while (cnt < (uint32_t)BATCH && scan_pos < p.n_tris) {
+                const uint32_t cand = scan_pos + lane;
+                bool hit = false;
+                if (cand < p.n_tris) {
+                    const uint2 bb = p.tri_bbox[cand];
+                    const uint32_t bx0 = bb.x & 0xffffu, bx1 = bb.x >> 16, by0 = max(bb.y & 0xffffu, p.row_begin), by1 = min(bb.y >> 16, p.row_end);
+                    hit = bx1 > bx0 && by1 > by0 && bx0 < stx + TILE && bx1 > stx && by0 < sty + TILE && by1 > sty &&
+                          (p.layers == 1u || draw_of(p, find_draw(p, cand)).layer == lay);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                const uint32_t take = min((uint32_t)__popc(m), (uint32_t)BATCH - cnt);
+                if (lane >= cnt && lane < cnt + take) id0 = scan_pos + __fns(m, 0u, (int)(lane - cnt) + 1);
+                if (take < (uint32_t)__popc(m)) {  // the round is full: resume after the last hit taken
+                    scan_pos += __fns(m, 0u, (int)take) + 1u;
+                    cnt += take;
+                    break;
+                }
+                cnt += take;
+                scan_pos += 32u;
+            }
+            if (cnt == 0u) break;
+            max_list += cnt;
+        }
         const uint32_t cnt0 = min(cnt, (uint32_t)BATCH), cnt1 = cnt - cnt0;
-        const uint32_t id0 = batch_id(NB * rd), id1 = cnt1 ? batch_id(NB * rd + 1u) : 0u;
 #ifdef EUC_RECS_TMA
         if (lane == 0) mbar_expect_tx(&bar[0], cnt * SW * 4u);
         __syncwarp();
@@ -1826,7 +1873,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
             const uint32_t lay = tk / per_layer;
             const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
             if (tile >= n_tiles) break;
-            const uint2 res = raster_tile<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list);
+            const uint32_t cnt_raw = p.bin_cap ? p.tile_count[tile] : 0u;
+            const bool lost = (cnt_raw & TILE_LOST) != 0u;  // warp-uniform, next to never
+            const uint2 res = lost ? raster_tile<P, MSAA, DEFER, LINES, true>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list, cnt_raw)
+                                   : raster_tile<P, MSAA, DEFER, LINES, false>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list, cnt_raw);
             phase = res.x;
             nfrag += res.y;
             __syncwarp();

@@ -188,8 +188,9 @@ int euc_sync(euc_ctx* ctx);
  * reaches it through mapped pinned memory.  Consequences for errors that only the device can detect: a vertex index out
  * of range in geometry whose index bounds the host has not seen (euc_geom_wrap; euc_geom_update / euc_render with more
  * than 65536 indices) makes that render draw nothing and is reported as EUC_E_OUT_OF_BOUNDS by the NEXT call on the
- * context (render, euc_sync, download, euc_get_stats); exhaustion of the bin-overflow buffer likewise as EUC_E_OOM (the
- * buffer is then larger: re-issue the frame).  Geometry created with euc_geom_create, small index streams and non-indexed
+ * context (render, euc_sync, download, euc_get_stats).  A scene far denser than the ones its target has seen cannot fail:
+ * tiles whose pairs fit neither their bin nor the overflow buffer are rendered by testing every primitive of the render
+ * against the tile (slow for that one render; the buffers are sized for it afterwards).  Geometry created with euc_geom_create, small index streams and non-indexed
  * streams are validated on the host and fail in the render call itself, like the reference's slice-index panic
  * (src/index.rs:53).  The first render of a target shape, and every render after euc_set_async(ctx, 0), is checked:
  * the call waits for the set-up kernel's flags (not for the raster work).  A whole frame of asynchronous single-draw

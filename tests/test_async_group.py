@@ -82,6 +82,35 @@ def test_bin_overflow_is_handled_on_the_device_without_a_host_wait():
     ctx.close()
 
 
+def test_overflow_of_the_overflow_buffer_falls_back_to_scanning_all_primitives(monkeypatch):
+    """A scene far denser than anything the target has seen: pairs fit neither the bins nor the (here: tiny) overflow buffer.
+    The affected tiles are rendered by testing every primitive against the tile; nothing fails, nothing waits."""
+    monkeypatch.setenv("EUC_OVF_ENTRIES", "64")
+    ctx = e.Context(0)
+    monkeypatch.delenv("EUC_OVF_ENTRIES")
+    w, h = 640, 64
+    px = e.Buffer2d([w, h], np.uint32, ctx)
+    z = e.Buffer2d([w, h], np.float32, ctx)
+    pipe = e.BlendTris()
+    n = 3000
+    pipe.render(_spread_tris(n, 1), px, z, clear=(0xFF000000, 1.0))
+    ctx.sync()
+    waits = ctx.blocking_waits()
+    for k in range(2):
+        v = _stacked_tris(n, 4321 + k)
+        ctx.set_stats(True)
+        pipe.render(v, px, z, clear=(0xFF000000, 1.0))
+        st = ctx.get_stats()
+        ctx.set_stats(False)
+        rpx, rz, rs = _oracle_frame(v, w, h)
+        assert st["fragments"] == rs["fragments"]
+        assert_depth_bit_exact(z.raw(), rz, f"scan pass {k}")
+        assert_colour_within_1lsb(px.raw(), rpx, f"scan pass {k}")
+    assert ctx.blocking_waits() == waits
+    del px, z
+    ctx.close()
+
+
 def test_checked_mode_still_redoes_overflowing_renders_on_the_exact_path():
     ctx = e.Context(0)
     ctx.set_async(False)

@@ -177,3 +177,41 @@ def test_gpu_lines_msaa_and_line_triangle_list():
     assert rs["primitives"] == 600  # 200 collected triangles x 3 lines
     assert np.array_equal(px.raw() != 0, rpx != 0)
     assert_colour_within_1lsb(px.raw(), rpx, "msaa lines")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [e.LineList, e.LineTriangleList])
+def test_gpu_lines_for_immediate_mode_pipeline(kind):
+    """primitives.rs:49-104 is generic over the pipeline: a blending (immediate-mode) pipeline draws lines in submission
+    order too.  BLEND_TRIS has no transcendental: colour bit-exact."""
+    from conftest import assert_depth_bit_exact
+    w, h = 800, 300
+    v = _random_lines(450, 21, False)
+    pipe = lambda: e.BlendTris(primitives=kind, depth=e.DepthMode.LESS_WRITE)
+    px, z = e.Buffer2d.fill([w, h], 0xFF000000, dtype=np.uint32), e.Buffer2d.fill([w, h], 1.0)
+    pipe().render(v, px, z)
+    rpx, rz = np.full((h, w), 0xFF000000, np.uint32), np.full((h, w), 1.0, np.float32)
+    rs = oracle.render(pipe(), v, rpx, rz, n_threads=0)
+    assert rs["fragments"] > 1000
+    assert_depth_bit_exact(z.raw(), rz, "blend lines depth")
+    assert np.array_equal(px.raw(), rpx), "blend lines colour"
+
+
+@pytest.mark.gpu
+def test_gpu_phong_wireframe_teapot():
+    """The teapot drawn as LineTriangleList through the Phong pipeline (nine varyings, shadow-map sampler): every pipeline
+    with a fragment stage renders lines."""
+    from conftest import assert_colour_within_1lsb, assert_depth_bit_exact
+    w, h, s = 640, 480, 512
+    stream, u = scenes.teapot_stream(), scenes.teapot_uniforms(w, h, s)
+    shadow = e.Buffer2d.fill([s, s], 1.0)
+    e.TeapotShadow(u["shadow_mvp"]).render(stream, e.Empty(), shadow)
+    mk = lambda smp: e.Teapot(u["m"], u["v"], u["p"], u["light_pos"], smp, u["light_vp"], u["cam_pos"], primitives=e.LineTriangleList)
+    px, z = e.Buffer2d.fill([w, h], 0, dtype=np.uint32), e.Buffer2d.fill([w, h], 1.0)
+    mk(shadow.linear().clamped()).render(stream, px, z)
+    r_shadow = shadow.raw()
+    rpx, rz = np.zeros((h, w), np.uint32), np.full((h, w), 1.0, np.float32)
+    rs = oracle.render(mk(e.Sampler(r_shadow, e.abi.TEXEL_F32, e.abi.FILTER_LINEAR).clamped()), stream, rpx, rz, n_threads=0)
+    assert rs["fragments"] > 20000
+    assert_depth_bit_exact(z.raw(), rz, "phong wireframe depth")
+    assert_colour_within_1lsb(px.raw(), rpx, "phong wireframe colour")

@@ -94,6 +94,23 @@ def test_user_deferred_pipeline_matches_vertex_color(aa):
 
 
 @pytest.mark.gpu
+def test_user_pipeline_draws_lines():
+    """Run-time pipelines accept LineList / LineTriangleList like the built-in ones."""
+    ctx = e.default_context()
+    pid = ctx.register_pipeline(DEFERRED_SRC, "UserVertexColor")
+    w, h = 640, 360
+    verts = _tris(300, 11)
+    kw = dict(depth=e.DepthMode.LESS_WRITE, primitives=e.LineTriangleList)
+    px, z = e.Buffer2d.fill([w, h], 0, dtype=np.uint32), e.Buffer2d.fill([w, h], 1.0)
+    e.UserPipeline(pid, e.VERTEX_P4C4, np.eye(4, dtype=np.float32).tobytes(), **kw).render(verts, px, z)
+    rpx, rz = np.zeros((h, w), np.uint32), np.full((h, w), 1.0, np.float32)
+    rs = oracle.render(e.VertexColor(**kw), verts, rpx, rz, n_threads=0)
+    assert rs["primitives"] == 900 and rs["fragments"] > 5000
+    assert_depth_bit_exact(z.raw(), rz, "user pipeline lines")
+    assert_colour_within_1lsb(px.raw(), rpx, "user pipeline lines")
+
+
+@pytest.mark.gpu
 def test_user_pipeline_compile_error_is_reported():
     ctx = e.default_context()
     with pytest.raises(e.EucError) as ei:

@@ -1,6 +1,7 @@
 """Randomised differential soak: random scenes (sizes, depth / cull / coordinate modes, MSAA levels, pipelines, hostile
 vertices, fused clears) rendered by the CUDA path and by the CPU oracle; depth and fragment counts must be bit-exact,
-colour within 1 LSB.  Not part of the test suite (open-ended); usage: python tools/fuzz_parity.py [seconds] [seed]"""
+colour within 1 LSB.  Open-ended run: python tools/fuzz_parity.py [seconds] [seed].  tests/test_fuzz_slice.py runs a fixed
+200-scene slice of the same generators (triangle_scene / sampler_or_line_scene) in the `-m gpu` suite."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,14 +10,11 @@ import euc_b200 as e
 from euc_b200 import scenes
 from oracle import oracle
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-ctx = e.default_context(); ctx.set_stats(True)
-t_end = time.time() + budget
-n_scenes = n_frag = 0
-k = 0
-while time.time() < t_end:
-    k += 1
+
+
+def triangle_scene(k, seed0):
+    """One random triangle scene through both paths; returns the fragment count.  Raises AssertionError on a mismatch."""
+    ctx = e.default_context(); ctx.set_stats(True)
     rng = np.random.default_rng(seed0 * 100003 + k)
     w = int(rng.choice([64, 100, 333, 640, 1000, 1920, 2500, 4096])); h = int(rng.choice([48, 64, 217, 480, 720]))
     n = int(rng.choice([1, 7, 60, 400, 3000]))
@@ -65,14 +63,13 @@ while time.time() < t_end:
         assert np.array_equal(gz.view(np.uint32), rz.view(np.uint32)), what + " depth differs"
     dmax = np.abs(gpx.view(np.uint8).astype(np.int16) - rpx.view(np.uint8).astype(np.int16)).max()
     assert dmax <= 1, what + f" colour differs by {dmax}"
-    n_scenes += 1; n_frag += rs["fragments"]
-print(f"fuzz ok: {n_scenes} triangle scenes, {n_frag} fragments, seed {seed0}, {budget:.0f} s")
+    return rs["fragments"]
+
 
 # ---- samplers (textured cube, random texture / filter / wrap / uv scale / pose) and lines -------------------------------
-t_end = time.time() + budget / 3
-n_cube = n_lines = 0
-while time.time() < t_end:
-    k += 1
+def sampler_or_line_scene(k, seed0):
+    """One random textured-cube or line-list scene through both paths; returns "cube" or "lines"."""
+    ctx = e.default_context(); ctx.set_stats(True)
     rng = np.random.default_rng(seed0 * 100003 + k)
     w = int(rng.choice([320, 640, 1000, 1920])); h = int(rng.choice([200, 480, 1080]))
     if rng.random() < 0.6:
@@ -95,7 +92,7 @@ while time.time() < t_end:
         rpx = np.full((h, w), 180, np.uint32)
         rs = oracle.render(make(tex), e.IndexedVertices(idx, verts), rpx, None, n_threads=0)
         what = f"cube scene {k} seed {seed0}: {w}x{h} tex {tw}x{th} {filt} {wrap}"
-        n_cube += 1
+        which = "cube"
     else:
         n = int(rng.choice([2, 20, 400]))
         v = np.zeros(2 * n, dtype=e.VERTEX_P4C4)
@@ -114,8 +111,25 @@ while time.time() < t_end:
         what = f"line scene {k} seed {seed0}: {w}x{h} n={n} {depth}"
         if rz is not None:
             assert np.array_equal(z.raw().view(np.uint32), rz.view(np.uint32)), what + " depth differs"
-        n_lines += 1
+        which = "lines"
     assert gfr == rs["fragments"], what + f" fragments {gfr} != {rs['fragments']}"
     dmax = np.abs(px.raw().view(np.uint8).astype(np.int16) - rpx.view(np.uint8).astype(np.int16)).max()
     assert dmax <= 1, what + f" colour differs by {dmax}"
-print(f"fuzz ok: {n_cube} textured-cube scenes, {n_lines} line scenes")
+    return which
+
+
+if __name__ == "__main__":
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    t_end = time.time() + budget
+    n_scenes = n_frag = k = 0
+    while time.time() < t_end:
+        k += 1
+        n_frag += triangle_scene(k, seed0); n_scenes += 1
+    print(f"fuzz ok: {n_scenes} triangle scenes, {n_frag} fragments, seed {seed0}, {budget:.0f} s")
+    t_end = time.time() + budget / 3
+    counts = {"cube": 0, "lines": 0}
+    while time.time() < t_end:
+        k += 1
+        counts[sampler_or_line_scene(k, seed0)] += 1
+    print(f"fuzz ok: {counts['cube']} textured-cube scenes, {counts['lines']} line scenes")

@@ -9,8 +9,10 @@ tu = '#include "kernels.cuh"\nnamespace eucb {\n#line 1 "user_pipeline.cu"\n' + 
 n = C.CDLL(os.environ.get("NVRTC_LIB", "/usr/local/cuda/lib64/libnvrtc.so.12"))
 prog = C.c_void_p()
 assert n.nvrtcCreateProgram(C.byref(prog), tu.encode(), b"euc_user_pipeline.cu", 0, None, None) == 0
-names = [b"eucb::setup_kernel<EucUserPipe>", b"eucb::raster_kernel<EucUserPipe, false, EUC_USER_DEFER, false>", b"eucb::raster_kernel<EucUserPipe, true, EUC_USER_DEFER, false>",
-         b"eucb::resolve_kernel<EucUserPipe, false, false>", b"eucb::resolve_kernel<EucUserPipe, true, false>"]
+names = [b"eucb::setup_kernel<EucUserPipe, false>", b"eucb::raster_kernel<EucUserPipe, false, EUC_USER_DEFER, false>", b"eucb::raster_kernel<EucUserPipe, true, EUC_USER_DEFER, false>",
+         b"eucb::resolve_kernel<EucUserPipe, false, false>", b"eucb::resolve_kernel<EucUserPipe, true, false>",
+         b"eucb::setup_lines_kernel<EucUserPipe>", b"eucb::raster_kernel<EucUserPipe, false, EUC_USER_DEFER, true>", b"eucb::raster_kernel<EucUserPipe, true, EUC_USER_DEFER, true>",
+         b"eucb::resolve_kernel<EucUserPipe, false, true>", b"eucb::resolve_kernel<EucUserPipe, true, true>"]
 for nm in names:
     n.nvrtcAddNameExpression(prog, nm)
 opts = [b"--gpu-architecture=sm_100a", b"--fmad=false", b"-std=c++17", b"-lineinfo", b"-device-int128", b"-default-device",
