@@ -1001,9 +1001,9 @@ template <class P, bool DEFER> struct StageGeom {
     static constexpr uint32_t WORDS = BATCHES * BATCH * REC_WORDS;                                           // stage words per warp
 };
 
-// per warp: record stage | 16 B (mbarriers) | per-lane fragment queues | per-lane colour rows
+// per warp: record stage | 16 B (mbarriers) | 32 B (tiles noted for the slow pass) | per-lane fragment queues | per-lane colour rows
 template <class P, bool DEFER> struct WarpSmem {
-    static constexpr uint32_t BYTES = StageGeom<P, DEFER>::WORDS * 4u + 16u + ((!DEFER && P::HAS_FRAGMENT) ? 32u * (Q_STRIDE_WORDS + COL_STRIDE) * 4u : 0u);
+    static constexpr uint32_t BYTES = StageGeom<P, DEFER>::WORDS * 4u + 48u + ((!DEFER && P::HAS_FRAGMENT) ? 32u * (Q_STRIDE_WORDS + COL_STRIDE) * 4u : 0u);
 };
 template <class P, bool DEFER> constexpr size_t raster_smem_bytes() { return (size_t)RASTER_WARPS * WarpSmem<P, DEFER>::BYTES; }
 
@@ -1176,9 +1176,9 @@ __device__ __forceinline__ void px_step(float& d, uint32_t& cwj, float& w0, floa
 // One 16x16 tile, walked by one warp.
 // Not inlined on purpose: inside the persistent loop the register allocation of the (large) tile body got worse.
 // Returns (mbarrier phase after the tile, fragments emitted).
-template <class P, bool MSAA, bool DEFER, bool LINES, bool SCAN>
+template <class P, bool MSAA, bool DEFER, bool LINES, bool SLOW>
 __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
-                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, uint32_t& max_list, const uint32_t cnt_raw) {
+                                          uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, const uint32_t cnt_raw) {
     using L = RecLayout<P>;
     uint32_t nfrag = 0;
     constexpr uint32_t SW = StageGeom<P, DEFER>::REC_WORDS;
@@ -1186,9 +1186,10 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     constexpr bool QUEUE = !DEFER && P::HAS_FRAGMENT;
     uint2 rg;
     uint32_t n_bin;  // entries of the list that live in the tile's own bin / slice; the rest (bin overflow) in `ext`
-    // SCAN: the tile's list is incomplete (TILE_LOST): every primitive of the render is tested against the tile.  A separate
-    // instantiation, so that the ordinary tile loop carries none of its state.
-    constexpr bool scan_all = SCAN;
+    // SLOW: the tile's bin overflowed.  Either the rest of its list sits in the overflow buffer (collected into `ext`
+    // below), or pairs were dropped (TILE_LOST) and every primitive of the render is tested against the tile.  A separate
+    // instantiation, run after the ordinary tiles, so that the ordinary tile loop carries none of this.
+    const bool scan_all = SLOW && (cnt_raw & TILE_LOST) != 0u;
     if (p.bin_cap) {
         const uint32_t cnt_t = cnt_raw & ~TILE_LOST;  // cnt_raw: tile_count[tile], read by the caller
         rg = make_uint2(tile * p.bin_cap, scan_all ? 1u : cnt_t);
@@ -1200,7 +1201,9 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         n_bin = rg.y;
     }
     const uint32_t n = rg.y;
-    max_list = max(max_list, n);
+    // lists that come close to the bin size are reported (the host then enlarges the bins of later renders); no running maximum
+    // is carried through the tile loop
+    if (p.summary && n * 4u > p.bin_cap * 3u && lane == 0) atomicMax(p.counters + 7, (unsigned long long)n);
     if (n == 0) {
         // A tile without primitives still owes its rows to the mirrors (fused gather; immediate-mode pipelines, deferred
         // ones forward from resolve_kernel) and, under a fused clear, the clear values to its own targets.
@@ -1254,7 +1257,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     const bool short_list = n <= (uint32_t)IDS_REGS;
     uint32_t* const bin = p.tile_list + rg.x;
     uint32_t* ext = nullptr;
-    if (!scan_all && n > n_bin) {
+    if (SLOW && !scan_all && n > n_bin) {
         // The bin overflowed (warp-uniform, rare: the host sizes the bins from the lists of earlier renders).  The pairs
         // that did not fit are somewhere in the overflow buffer: take a slice of `ext` and collect this tile's pairs.
         uint32_t base_e = 0;
@@ -1272,9 +1275,9 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         }
         __syncwarp();
     }
-    auto lst = [&](uint32_t i) -> uint32_t& { return i < n_bin ? bin[i] : ext[i - n_bin]; };
+    auto lst = [&](uint32_t i) -> uint32_t& { return (!SLOW || i < n_bin) ? bin[i] : ext[i - n_bin]; };
     uint32_t v[4];
-    if (scan_all) {
+    if (SLOW && scan_all) {
         v[0] = v[1] = v[2] = v[3] = 0u;  // ids come from the scan below, already in submission order
     } else if (short_list) {
 #pragma unroll
@@ -1378,12 +1381,12 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     // primitives of the round.  Longer rounds bring the busiest lane closer to the mean (the round ends when the last
     // lane is done); the load of the next round is hidden by the other warps of the SM.
     constexpr uint32_t ROUND = NB * BATCH;
-    const uint32_t n_rounds = scan_all ? 0xffffffffu : (n + ROUND - 1) / ROUND;
+    const uint32_t n_rounds = (SLOW && scan_all) ? 0xffffffffu : (n + ROUND - 1) / ROUND;
     uint32_t scan_pos = 0;  // scan mode: next primitive id to test
     for (uint32_t rd = 0; rd < n_rounds; ++rd) {
         __syncwarp();  // every lane is done with the records of the previous round
         uint32_t cnt, id0, id1 = 0u;
-        if (!scan_all) {
+        if (!SLOW || !scan_all) {
             cnt = min(ROUND, n - rd * ROUND);
             id0 = batch_id(NB * rd);
             if (cnt > (uint32_t)BATCH) id1 = batch_id(NB * rd + 1u);
@@ -1414,7 +1417,6 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
                 scan_pos += 32u;
             }
             if (cnt == 0u) break;
-            max_list += cnt;
         }
         const uint32_t cnt0 = min(cnt, (uint32_t)BATCH), cnt1 = cnt - cnt0;
 #ifdef EUC_RECS_TMA
@@ -1844,6 +1846,15 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
 
 // Persistent kernel: every warp takes tiles from a ticket counter until none are left, so the grid is sized by the
 // machine (SMs x resident CTAs), not by the frame, and there is no partial last wave.
+// Tiles whose bin overflowed take another instantiation of the tile loop (SLOW).  They are rare (the host sizes the bins from
+// the lists of earlier renders), and the ordinary loop must not pay for them with registers or instruction-cache space: a warp
+// only notes such a tile and comes back to it after its ordinary tiles.
+constexpr uint32_t SLOW_SLOTS = 7;
+template <class P, bool MSAA, bool DEFER, bool LINES>
+__device__ __noinline__ uint2 raster_tile_slow(const Params& p, const uint32_t tile, const uint32_t lane, uint32_t* const recs_sm, uint64_t* const bar,
+                                               uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, const uint32_t cnt_raw) {
+    return raster_tile<P, MSAA, DEFER, LINES, true>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, cnt_raw);
+}
 template <class P, bool MSAA, bool DEFER, bool LINES>
 __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_RASTER_MIN_CTAS) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
     using L = RecLayout<P>;
@@ -1853,32 +1864,53 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
     uint8_t* const warp_sm = smem_raw + (size_t)warp * WarpSmem<P, DEFER>::BYTES;
     uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(warp_sm);
     uint64_t* const bar = reinterpret_cast<uint64_t*>(warp_sm + STW * 4);
-    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 16);
+    uint32_t* const slow = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 16);  // [0]: noted tiles, [1 ..]: their indices
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 48);
     uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
     uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); slow[0] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t phase = 0, nfrag = 0, max_list = 0;
+    uint32_t phase = 0, nfrag = 0;
     if (!render_aborted(p)) {
         unsigned int* const ticket = reinterpret_cast<unsigned int*>(p.counters + 4);
         // tickets enumerate only the tile rows that intersect the rendered rows [row_begin, row_end)
         const uint32_t ty_lo = p.row_begin / TILE, ty_hi = (min(p.row_end, p.h) + TILE - 1) / TILE;
         const uint32_t per_layer = (ty_hi - ty_lo) * p.tiles_x, n_active = per_layer * p.layers;
-        for (;;) {
-            uint32_t tk = 0;
-            if (lane == 0) tk = atomicAdd(ticket, 1u);
-            tk = __shfl_sync(0xffffffffu, tk, 0);
-            if (tk >= n_active) break;
-            const uint32_t lay = tk / per_layer;
-            const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
-            if (tile >= n_tiles) break;
-            const uint32_t cnt_raw = p.bin_cap ? p.tile_count[tile] : 0u;
-            const bool lost = (cnt_raw & TILE_LOST) != 0u;  // warp-uniform, next to never
-            const uint2 res = lost ? raster_tile<P, MSAA, DEFER, LINES, true>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list, cnt_raw)
-                                   : raster_tile<P, MSAA, DEFER, LINES, false>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, max_list, cnt_raw);
-            phase = res.x;
-            nfrag += res.y;
+        for (bool more = true; more;) {
+            more = false;
+            for (;;) {
+                uint32_t tk = 0;
+                if (lane == 0) tk = atomicAdd(ticket, 1u);
+                tk = __shfl_sync(0xffffffffu, tk, 0);
+                if (tk >= n_active) break;
+                const uint32_t lay = tk / per_layer;
+                const uint32_t tile = lay * p.tiles_x * p.tiles_y + ty_lo * p.tiles_x + (tk - lay * per_layer);
+                if (tile >= n_tiles) break;
+                const uint32_t cnt_raw = p.bin_cap ? p.tile_count[tile] : 0u;
+                if (cnt_raw > p.bin_cap) {  // (only with bins) overflowed, or marked TILE_LOST: later
+                    const uint32_t k = slow[0];
+                    __syncwarp();
+                    if (lane == 0) { slow[1u + k] = tile; slow[0] = k + 1u; }
+                    __syncwarp();
+                    if (k + 1u == SLOW_SLOTS) { more = true; break; }
+                    continue;
+                }
+                const uint2 res = raster_tile<P, MSAA, DEFER, LINES, false>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, cnt_raw);
+                phase = res.x;
+                nfrag += res.y;
+                __syncwarp();
+            }
+            const uint32_t n_slow = slow[0];
+            for (uint32_t i = 0; i < n_slow; ++i) {
+                const uint32_t tile = slow[1u + i];
+                const uint2 res = raster_tile_slow<P, MSAA, DEFER, LINES>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, p.tile_count[tile]);
+                phase = res.x;
+                nfrag += res.y;
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) slow[0] = 0u;
             __syncwarp();
         }
         if (p.stats) {
@@ -1893,7 +1925,6 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
     // Summary for the host: the last warp of the grid to get here publishes flags / longest list / overflow volume into
     // mapped pinned memory, so that the host can size the bins of later renders without ever waiting for this one.
     if (p.summary && lane == 0) {
-        if (max_list) atomicMax(p.counters + 7, (unsigned long long)max_list);
         __threadfence();
         const unsigned long long done = atomicAdd(p.counters + 8, 1ull) + 1ull;
         if (done == (unsigned long long)gridDim.x * RASTER_WARPS) {
