@@ -87,7 +87,6 @@ struct euc_ctx {
     // Smallest group whose ranks classify the primitives together (sort-middle of ids, group.inc) instead of each setting up
     // the whole stream; 0 = never.  EUC_GROUP_CLS_MIN_WORLD overrides (tests use 2).
     uint32_t group_cls_min_world = 0;
-    bool raster2 = true;     // EUC_RASTER2=0: immediate-mode pipelines use the first form of the tile kernel (A/B runs)
     uint64_t ovf_fixed = 0;  // EUC_OVF_ENTRIES (tests): fixed size of the bin-overflow buffer instead of the adaptive one
     euc_render_stats last{};
     bool stats_on_device = false;  // the fragment counter of the last render lives in counters[1]
@@ -540,12 +539,7 @@ template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx, 
         else setup_kernel<P, false><<<blocks, 128, 0, ctx->stream>>>(prm);
     };
     if (!LINES) ops.group_classify = [ctx](const Params& prm, uint32_t blocks) { group_classify_kernel<P><<<blocks, 256, 0, ctx->stream>>>(prm); };
-    // immediate-mode triangle pipelines without MSAA take the second form of the tile kernel (raster2.cuh)
-    constexpr bool R2 = !DEFER && !LINES && P::HAS_FRAGMENT && StageGeom<P, DEFER>::BATCHES == 1;
     ops.raster = [ctx](const Params& prm, bool msaa, uint32_t blocks, uint32_t n_tiles) {
-        if constexpr (R2) {
-            if (!msaa && ctx->raster2) { raster2_kernel<P><<<blocks, RASTER_WARPS * 32, raster2_smem_bytes<P>(), ctx->stream>>>(prm, n_tiles); return; }
-        }
         auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
         kern<<<blocks, RASTER_WARPS * 32, raster_smem_bytes<P, DEFER>(), ctx->stream>>>(prm, n_tiles);
     };
@@ -553,20 +547,8 @@ template <class P, bool LINES = false> const PipeOps& builtin_ops(euc_ctx* ctx, 
         if (msaa) resolve_kernel<P, true, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
         else resolve_kernel<P, false, LINES><<<grid, 128, 0, ctx->stream>>>(prm);
     };
-    ops.resident = [po, ctx](bool msaa) -> int {
+    ops.resident = [po](bool msaa) -> int {
         int* res = po->resident_cache;
-        if constexpr (R2) {
-            if (!msaa && ctx->raster2) {
-                if (!res[0]) {
-                    const size_t smem2 = raster2_smem_bytes<P>();
-                    if (cudaFuncSetAttribute(raster2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) return -1;
-                    int nb = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, raster2_kernel<P>, RASTER_WARPS * 32, smem2) != cudaSuccess) return -1;
-                    res[0] = std::max(nb, 1);
-                }
-                return res[0];
-            }
-        }
         if (!res[msaa]) {
             auto kern = msaa ? raster_kernel<P, true, DEFER, LINES> : raster_kernel<P, false, DEFER, LINES>;
             const size_t smem = raster_smem_bytes<P, DEFER>();
@@ -868,7 +850,6 @@ int euc_init(int device_ordinal, euc_ctx** out_ctx) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     if (const char* e = getenv("EUC_SPARSE_RECS")) ctx->sparse_recs = atoi(e);
     if (const char* e = getenv("EUC_GROUP_CLS_MIN_WORLD")) ctx->group_cls_min_world = (uint32_t)std::max(atoi(e), 0);
-    if (const char* e = getenv("EUC_RASTER2")) ctx->raster2 = atoi(e) != 0;
     if (const char* e = getenv("EUC_OVF_ENTRIES")) ctx->ovf_fixed = (uint64_t)std::max(atoll(e), 0ll);
     *out_ctx = ctx;
     return EUC_OK;

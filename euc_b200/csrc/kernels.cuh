@@ -2061,5 +2061,3 @@ template <class P, bool MSAA, bool LINES> __global__ void __launch_bounds__(128)
 }
 
 }  // namespace eucb
-
-#include "raster2.cuh"
