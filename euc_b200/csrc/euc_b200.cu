@@ -37,7 +37,17 @@ struct Geom {
     // nothing to wait for.  Unknown bounds: the device checks, and the error is deferred (see euc_set_async).
     bool bounds_known = false;
     uint32_t idx_min = 0, idx_max = 0;
+    // A draw table (batch rendering: ranges + base vertices) that the global bounds cannot prove in range is checked once on
+    // the device; the same table on the same indices need not be checked again.
+    uint64_t version = 0;
+    mutable uint64_t verified_hash = 0, verified_version = ~0ull;
 };
+uint64_t fnv1a(const void* data, size_t n) {
+    const uint8_t* b = (const uint8_t*)data;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h ? h : 1;
+}
 // Index bounds of a host index array (one pass; auto-vectorised)
 void index_bounds(const uint32_t* idx, size_t n, uint32_t& lo, uint32_t& hi) {
     uint32_t a = 0xffffffffu, b = 0u;
@@ -695,6 +705,11 @@ int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
         dd[i] = DrawDev{b.first, b.count, b.base_vertex, b.layer, (uint32_t)tri_total, nprim};
         tri_total += nprim;
     }
+    uint64_t draws_hash = 0;
+    if (rc.maybe_oob_sync) {
+        draws_hash = fnv1a(rc.draws, (size_t)rc.n_draws * sizeof(euc_batch_draw));
+        if (gm.verified_hash == draws_hash && gm.verified_version == gm.version) rc.maybe_oob_sync = false;  // this table was checked on these indices
+    }
     if (tri_total == 0) return plain_clear(true, true);
     if (tri_total > 0x7fffffffull) return fail(ctx, EUC_E_UNSUPPORTED, "too many primitives");
 
@@ -800,6 +815,7 @@ int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
     prm.tile_range = (uint2*)ctx->tile_range.p;
 
     if (user_pipe) return render_driver(ctx, rc, prm, n_tiles, lines ? user_pipe->ops_lines : user_pipe->ops);
+    const uint64_t waits_before = ctx->blocking_waits;
 #define EUC_DISPATCH(P) rcode = lines ? render_typed<P, true>(ctx, rc, prm, n_tiles) : render_typed<P>(ctx, rc, prm, n_tiles); break
     switch (d.pipeline_id) {
         case EUC_PIPE_TEAPOT_SHADOW: EUC_DISPATCH(PipeTeapotShadow);
@@ -812,6 +828,8 @@ int render_common(euc_ctx* ctx, const RenderCall& rc_in) {
         default: rcode = EUC_E_INVALID;
     }
 #undef EUC_DISPATCH
+    // a checked render that found every index in range: its draw table need not be checked again on these indices
+    if (rcode == EUC_OK && rc.maybe_oob_sync && ctx->blocking_waits > waits_before) { gm.verified_hash = draws_hash; gm.verified_version = gm.version; }
     // dd is pageable: make sure the async copy consumed it (render_typed synchronises; early outs do not)
     return rcode;
 }
@@ -1155,6 +1173,7 @@ int euc_geom_update(euc_ctx* ctx, euc_geom geom, const void* vertices, const uin
         // over it): the device checks every index and an out-of-range one is reported by a later call (euc_set_async)
         g.bounds_known = g.n_idx <= HOST_SCAN_MAX_INDICES;
         if (g.bounds_known) index_bounds(indices, g.n_idx, g.idx_min, g.idx_max);
+        ++g.version;
     }
     return EUC_OK;
 }
@@ -1171,6 +1190,7 @@ int euc_geom_update_range(euc_ctx* ctx, euc_geom geom, const void* vertices, uin
     if (indices && n_indices) {
         CU(cudaMemcpyAsync(g.idx + first_index, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
         g.bounds_known = false;  // a part of the indices changed: the device checks (deferred error, see euc_set_async)
+        ++g.version;
     }
     return EUC_OK;
 }

@@ -24,8 +24,15 @@ for wl in ("c4","c1","c2","c3","c5"):
 print(open("gpurun_out/${TAG}_bench_ref_c4.json").read()[:400])
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_launches_c4.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-icon-batch > gpurun_out/ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_raster_c4 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-icon-batch > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:setup_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_setup_c4 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-icon-batch > gpurun_out/ncu_full2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:resolve_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_resolve_c3 -f python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_raster_c5 -f python bench.py --workload c5 --icons 1024 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full4.log 2>&1
-ls gpurun_out | grep ${TAG}_ | head -40
+capture() {  # capture <kernel regex> <name> <bench args...>: full ncu capture, exported as raw + source CSV pages (the .ncu-rep files exceed what comes back)
+  local k=$1 name=$2; shift 2
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/${TAG}_$name -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ncu_$name.log 2>&1
+  ncu -i gpurun_out/${TAG}_$name.ncu-rep --page raw --csv > gpurun_out/${TAG}_${name}_full_raw.csv 2>/dev/null
+  ncu -i gpurun_out/${TAG}_$name.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${TAG}_${name}_source.csv 2>/dev/null
+  rm -f gpurun_out/${TAG}_$name.ncu-rep
+}
+capture raster_kernel raster_c4 --no-icon-batch
+capture setup_kernel setup_c4 --no-icon-batch
+capture resolve_kernel resolve_c3 --workload c3
+capture raster_kernel raster_c5 --workload c5 --icons 1024
+ls -la gpurun_out | grep ${TAG}_ | head -40

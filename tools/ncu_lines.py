@@ -3,7 +3,7 @@ instructions, average active threads per instruction, stall samples.
 usage: python tools/ncu_lines.py report.ncu-rep [top_n]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 45
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout  # a .csv = an exported source page
 rows = list(csv.reader(io.StringIO(out)))
 allrows, fname, ci = [], "?", None
 for r in rows:

@@ -6,7 +6,7 @@ regions = []
 for part in sys.argv[2].split(";"):
     name, rs = part.split(":")
     regions.append((name, [tuple(map(int, r.split("-"))) for r in rs.split(",")]))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout  # a .csv = an exported source page
 rows = list(csv.reader(io.StringIO(out)))
 ci = None
 acc = {n: [0.0, 0.0, 0.0] for n, _ in regions}

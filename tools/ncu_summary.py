@@ -1,6 +1,6 @@
 """Key counters of one ncu report (raw page): python tools/ncu_summary.py report.ncu-rep"""
 import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(sys.argv[1]).read() if sys.argv[1].endswith(".csv") else subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout  # a .csv = an exported raw page
 rows = list(csv.reader(out.splitlines()))
 h, u, v = rows[0], rows[1], rows[-1]
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
