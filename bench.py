@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--icons", type=int, default=4096, help="C5: icons in the whole job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-icon-batch", action="store_true", help="C4 runs only: skip the 4096-icon batch (BASELINE config 5) that rides along")
-    ap.add_argument("--icon-steps", type=int, default=5)
+    ap.add_argument("--icon-steps", type=int, default=None, help="batches timed for the icon batch that rides along (default: 20 per GPU, i.e. a timed region of about 65 ms)")
     return ap.parse_args()
 
 
@@ -713,7 +713,8 @@ def measure(wl, args, rank, world, local_rank, steps=None, warm=None, cpu_baseli
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and world == 1:  # ncu captures are single-GPU, whole-frame launches
-            traffic = json.load(open(tpath)).get(f"{wl}_{dom}", json.load(open(tpath)).get(wl) if dom == "raster" else None)
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"c5_{args.icons}_{dom}") if wl == "c5" else tj.get(f"{wl}_{dom}")
         kernel_names = {"raster": "raster_kernel", "resolve": "resolve_kernel", "setup": "setup_kernel", "alloc": "alloc_tiles_kernel", "fill": "fill_kernel", "classify": "band_classify_kernel"}
         line = {
             "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
@@ -766,7 +767,7 @@ def run_ours(args, rank, world, local_rank):
     line = measure(args.workload, args, rank, world, local_rank)
     if args.workload == "c4" and not args.no_icon_batch:
         # BASELINE config 5 rides along in the same record: 4096 icons strong-sharded over the job's GPUs
-        ib = measure("c5", args, rank, world, local_rank, steps=args.icon_steps, warm=3, cpu_baseline=False)
+        ib = measure("c5", args, rank, world, local_rank, steps=args.icon_steps if args.icon_steps is not None else 20 * world, warm=3, cpu_baseline=False)
         if rank == 0:
             line["icon_batch"] = {"workload": ib["config"]["workload"], "icons": args.icons, "n_gpus": world, "metric": "icons_per_s", "value": ib["value"], "unit": "icons/s",
                                   "ms_per_batch": ib["ms_per_step"], "e2e": ib["e2e"], "scaling": "strong", "partition": ib["config"]["partition"],
