@@ -734,6 +734,8 @@ def measure(wl, args, rank, world, local_rank, steps=None, warm=None, cpu_baseli
                          "traffic": traffic, "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_s * 1000.0, "launches_per_frame": dom_per_frame,
                          "peak_source": peak_src, "frame_frac": (alg / ((ms / steps) / 1000.0) / 1e9) / peak / (1 if wl != "c5" else 1),
                          "limiter": "instruction issue, not HBM (ncu: issue-active ~80 %, DRAM < 10 % of peak; profiles/)"},
+            "parity": {"checked_against": "oracle/ (C++ restatement of euc's render path) via the golden CRCs of tests/golden", "oracle_pinned": False,
+                       "why": "the reference is a Rust crate; no rustc / cargo here, so real euc never ran (DESIGN.md section 6)"},
             "stage_ms_per_launch": stage_ms,
             "stage_timing": "CUDA events around every kernel launch, " + ("inside the timed region" if prof_in_region else f"separate run of {prof_steps} frames (N > 1: the timed region carries no event pairs)"),
         }

@@ -135,3 +135,29 @@ def test_two_pass_teapot_with_shadow_map():
         res.append((shadow.raw().copy(), color.raw().copy(), depth.raw().copy()))
     for k, name in enumerate(("shadow map", "colour", "depth")):
         assert np.array_equal(res[0][k].view(np.uint32), res[1][k].view(np.uint32)), name
+
+
+def test_row_range_clear_of_an_odd_width_target():
+    """Round 1 returned EUC_E_UNSUPPORTED for a row range whose first texel is not 16-byte aligned (width not a multiple of 4:
+    the plain fill behind a clear the tile kernel cannot fuse, e.g. the colour target of a depth-only pass).  The fill now has
+    a scalar head and tail."""
+    w, h = 333, 160
+    verts = _random_tris(300, 5)
+    geom = e.Geometry(verts)
+    gc, gz = _garbage(w, h, 9)
+    c = e.Buffer2d([w, h], np.uint32); c.upload(gc)
+    d = e.Buffer2d([w, h], np.float32); d.upload(gz)
+    # depth-only use of the blending pipeline: pixel writes off, so the colour clear is a plain fill of rows [48, 112)
+    pipe = e.BlendTris(pixel=e.PixelMode.PASS, depth=e.DepthMode.LESS_WRITE)
+    pipe.render(geom, c, d, rows=(48, 112), clear=(PX, Z))
+    got_c, got_z = c.raw(), d.raw()
+    assert (got_c[48:112] == PX).all() and np.array_equal(got_c[:48], gc[:48]) and np.array_equal(got_c[112:], gc[112:])
+    ref_c = e.Buffer2d([w, h], np.uint32); ref_c.upload(gc)
+    ref_d = e.Buffer2d([w, h], np.float32); ref_d.upload(gz)
+    ref_d.clear_rows(Z, 48, 112)
+    pipe.render(geom, ref_c, ref_d, rows=(48, 112))
+    assert np.array_equal(got_z.view(np.uint32), ref_d.raw().view(np.uint32))
+    # and the stand-alone row clear on unaligned rows
+    c.clear_rows(7, 1, 2)
+    row = c.raw()
+    assert (row[1] == 7).all() and np.array_equal(row[0], got_c[0]) and np.array_equal(row[2], got_c[2])
