@@ -244,7 +244,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": warm, "ms_per_step": 1000.0 * float(np.mean(times)), "higher_is_better": True,
         "scaling": "weak" if wl == "c5" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl]["name"], "target": f"{WORKLOADS[wl]['w']}x{WORKLOADS[wl]['h']}",
+        "config": {"workload": WORKLOADS[wl]["name"], "target": f"{WORKLOADS[wl]['w']}x{WORKLOADS[wl]['h']}", "frames_per_step": 1 if wl != "c5" else args.icons,
+                   "clears": "every frame clears its targets (buffer fills, as the reference does)", "partition": "host cores (euc's own band threads)",
                    "note": "C++ restatement of euc's render_par (rustc unavailable here), all host cores; each step is the bounded sample"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
