@@ -910,6 +910,19 @@ __device__ __forceinline__ void bitonic_regs128(uint32_t (&v)[4], uint32_t lane)
     }
 }
 
+// The same for n <= 32 ids, one per lane (most tiles of an icon batch): 15 exchange steps instead of 100.
+__device__ __forceinline__ void bitonic_regs32(uint32_t& v, uint32_t lane) {
+#pragma unroll
+    for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? min(v, o) : max(v, o);
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
 // -------------------------------------------------------------------------------------------------------
@@ -971,6 +984,9 @@ constexpr int RASTER_WARPS = 4;
 #ifndef EUC_RASTER_MIN_CTAS
 #define EUC_RASTER_MIN_CTAS 7
 #endif
+#ifndef EUC_SORT32
+#define EUC_SORT32 1             // lists of up to 32 ids are sorted by a one-register network
+#endif
 #ifndef EUC_ROUND64_MAX_REC_BYTES
 #define EUC_ROUND64_MAX_REC_BYTES 128u
 #endif
@@ -985,8 +1001,20 @@ constexpr uint32_t NO_WINNER = 0xffffffffu;
 #ifndef EUC_Q_FRAGS
 #define EUC_Q_FRAGS 32
 #endif
-constexpr int Q_ENTRIES = EUC_Q_ENTRIES;  // entries per lane (u16); lane stride is odd in words -> conflict-free banks
-constexpr int Q_STRIDE_WORDS = (EUC_Q_ENTRIES / 2) | 1;
+// Records above EUC_Q_BIG_REC_BYTES (the voxel icons' 192 bytes) get a shorter FIFO: with 12 entries the warp's shared memory
+// is 8240 bytes and six CTAs fit an SM; with 10 it is 7984 and the seventh fits (the register budget allows seven): the icon
+// batch's tile kernel 2.59 -> 2.45 ms per 4096 icons.
+#ifndef EUC_Q_ENTRIES_BIG_REC
+#define EUC_Q_ENTRIES_BIG_REC 10
+#endif
+#ifndef EUC_Q_BIG_REC_BYTES
+#define EUC_Q_BIG_REC_BYTES 160u
+#endif
+template <class P> struct QGeom {
+    static constexpr int ENTRIES = RecLayout<P>::WORDS * 4u > EUC_Q_BIG_REC_BYTES ? EUC_Q_ENTRIES_BIG_REC : EUC_Q_ENTRIES;  // entries per lane (u16)
+    static constexpr int STRIDE_WORDS = (ENTRIES / 2) | 1;  // lane stride is odd in words -> conflict-free banks
+    static_assert(ENTRIES >= 2 && ENTRIES <= 2 * STRIDE_WORDS, "fragment FIFO geometry");
+};
 constexpr int Q_FRAGS = EUC_Q_FRAGS;      // stop generating once a lane holds this many fragments
 constexpr int COL_STRIDE = 9;     // colour row of a lane: 8 words + 1 pad
 
@@ -1002,8 +1030,9 @@ template <class P, bool DEFER> struct StageGeom {
 };
 
 // per warp: record stage | 16 B (mbarriers) | 32 B (tiles noted for the slow pass) | per-lane fragment queues | per-lane colour rows
+constexpr uint32_t WARP_CTRL_BYTES = 48u;
 template <class P, bool DEFER> struct WarpSmem {
-    static constexpr uint32_t BYTES = StageGeom<P, DEFER>::WORDS * 4u + 48u + ((!DEFER && P::HAS_FRAGMENT) ? 32u * (Q_STRIDE_WORDS + COL_STRIDE) * 4u : 0u);
+    static constexpr uint32_t BYTES = StageGeom<P, DEFER>::WORDS * 4u + WARP_CTRL_BYTES + ((!DEFER && P::HAS_FRAGMENT) ? 32u * (QGeom<P>::STRIDE_WORDS + COL_STRIDE) * 4u : 0u);
 };
 template <class P, bool DEFER> constexpr size_t raster_smem_bytes() { return (size_t)RASTER_WARPS * WarpSmem<P, DEFER>::BYTES; }
 
@@ -1282,6 +1311,11 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
     } else if (short_list) {
 #pragma unroll
         for (uint32_t r = 0; r < 4; ++r) v[r] = r * 32 + lane < n ? lst(r * 32 + lane) : 0xffffffffu;
+#if EUC_SORT32
+        if (n <= 32u) {  // v[1 .. 3] are all padding
+            if (n > 1) bitonic_regs32(v[0], lane);
+        } else
+#endif
         if (n > 1) bitonic_regs128(v, lane);
     } else {
         uint32_t np2 = 1;
@@ -1558,7 +1592,7 @@ __device__ __forceinline__ uint2 raster_tile(const Params& p, const uint32_t til
         uint32_t qn = 0, qf = 0;  // queued entries / fragments of this lane
         for (;;) {
             // ---- generate: coverage + depth for this lane's own triangles, until its queue is nearly full ----
-            while ((own0 | own1) && qn < (uint32_t)Q_ENTRIES && qf < (uint32_t)Q_FRAGS) {
+            while ((own0 | own1) && qn < (uint32_t)QGeom<P>::ENTRIES && qf < (uint32_t)Q_FRAGS) {
                 uint32_t t;
                 if (own0) { t = (uint32_t)__ffs((int)own0) - 1u; own0 &= own0 - 1u; }
                 else { t = (uint32_t)BATCH + (uint32_t)__ffs((int)own1) - 1u; own1 &= own1 - 1u; }
@@ -1855,6 +1889,9 @@ __device__ __noinline__ uint2 raster_tile_slow(const Params& p, const uint32_t t
                                                uint32_t phase, uint16_t* const queue, uint32_t* const col_sm, const uint32_t cnt_raw) {
     return raster_tile<P, MSAA, DEFER, LINES, true>(p, tile, lane, recs_sm, bar, phase, queue, col_sm, cnt_raw);
 }
+// Taking several tiles per ticket (one atomic and one round trip for the tile counters of a chunk) was measured on the icon
+// batch, where a warp walks hundreds of small or empty tiles, and lost twice: fixed chunks of eight -17 %, chunks that shrink
+// to single tiles towards the end -12.6 % (profiles/README.md); one tile per ticket stays.
 template <class P, bool MSAA, bool DEFER, bool LINES>
 __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_RASTER_MIN_CTAS) raster_kernel(const __grid_constant__ Params p, uint32_t n_tiles) {
     using L = RecLayout<P>;
@@ -1865,9 +1902,9 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MSAA && !DEFER) ? 4 : EUC_
     uint32_t* const recs_sm = reinterpret_cast<uint32_t*>(warp_sm);
     uint64_t* const bar = reinterpret_cast<uint64_t*>(warp_sm + STW * 4);
     uint32_t* const slow = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 16);  // [0]: noted tiles, [1 ..]: their indices
-    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + 48);
-    uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * Q_STRIDE_WORDS);   // this lane's fragment FIFO
-    uint32_t* const col_sm = lane_sm + 32 * Q_STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
+    uint32_t* const lane_sm = reinterpret_cast<uint32_t*>(warp_sm + STW * 4 + WARP_CTRL_BYTES);
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(lane_sm + lane * QGeom<P>::STRIDE_WORDS);   // this lane's fragment FIFO
+    uint32_t* const col_sm = lane_sm + 32 * QGeom<P>::STRIDE_WORDS + lane * COL_STRIDE;             // this lane's 8 colours
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); slow[0] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();

@@ -236,9 +236,14 @@ def test_group_render_gathers_row_bands(gather, n_quads):
         peers = grp.share(color)
         mode = e.abi.GATHER_ROOT if gather == "root" else e.abi.GATHER_ALL
         # Both ranks of this test share ONE GPU: a device-wide synchronising call (cudaMalloc / cudaFree of a scratch buffer) on
-        # one thread would wait for the other rank's barrier kernel, which spins until this rank arrives.  One plain render
-        # sizes the scratch buffers first.  (With one GPU per rank - the real configuration - the situation cannot arise.)
-        e.BlendTris().render(geom, color, depth, clear=(0xFF000000, 1.0))
+        # one thread would wait for the other rank's barrier kernel, which spins until this rank arrives.  Plain renders size
+        # the scratch buffers first: the first one also reports the longest tile list, from which the second one sizes the
+        # bins (with 2^17 primitives the lists outgrow the default bins; a bin buffer that grows inside the first group render
+        # stalls on the peer's barrier kernel until its 10 s time-out - seen once in a run of the full suite).  (With one GPU per rank - the real configuration - the situation
+        # cannot arise.)
+        for _ in range(3):
+            e.BlendTris().render(geom, color, depth, clear=(0xFF000000, 1.0))
+            ctx.sync()
         color.clear(0x11111111)
         ctx.sync()
         sync.wait()

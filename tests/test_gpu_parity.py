@@ -229,6 +229,40 @@ def test_voxel_icons_batch():
         assert_colour_within_1lsb(gpx[k], rpx, f"icon {k}")
 
 
+def test_many_layers_large_batch():
+    """A batch the size of the benchmark's icon batches: 1200 layers = 307200 tiles, two thirds of them empty, about 75 tiles per
+    warp of the persistent tile kernel.  Eight distinct icons repeated: the small batch (2048 tiles) is checked against the
+    oracle, and every layer of the large batch must equal the layer of its icon in the small one bit for bit - with the clears
+    fused into the render and without."""
+    nd, reps = 8, 150
+    verts, idx, draws, ubs = scenes.voxel_icon_batch(nd)
+    geom = e.Geometry(verts, idx)
+    pipe = e.VoxelIcon(np.eye(4), scenes.VOXEL_LIGHT_DIR)
+    small_c = e.Buffer2d.fill([256, 256], 0, dtype=np.uint32, layers=nd)
+    small_z = e.Buffer2d.fill([256, 256], 1.0, layers=nd)
+    pipe.render_batch(geom, draws, ubs, small_c, small_z)
+    sc, sz = small_c.raw(), small_z.raw()
+    for k in (0, 5):
+        rpx, rz = np.zeros((256, 256), dtype=np.uint32), np.full((256, 256), 1.0, dtype=np.float32)
+        first, count, base, _ = draws[k]
+        oracle.render(e.VoxelIcon(scenes.voxel_icon_mvp(k), scenes.VOXEL_LIGHT_DIR), e.IndexedVertices(idx, verts), rpx, rz, draw=(first, count, base))
+        assert_depth_bit_exact(sz[k], rz, f"icon {k}")
+        assert_colour_within_1lsb(sc[k], rpx, f"icon {k}")
+    n = nd * reps
+    ub = len(ubs) // nd
+    big_draws = [(int(draws[k % nd][0]), int(draws[k % nd][1]), int(draws[k % nd][2]), k) for k in range(n)]
+    big_ubs = b"".join(ubs[(k % nd) * ub:(k % nd + 1) * ub] for k in range(n))
+    for fused in (False, True):
+        # the fused form starts from garbage: every tile of every layer, empty or not, must be written by the render
+        big_c = e.Buffer2d.fill([256, 256], 0x12345678 if fused else 0, dtype=np.uint32, layers=n)
+        big_z = e.Buffer2d.fill([256, 256], 0.25 if fused else 1.0, layers=n)
+        pipe.render_batch(geom, big_draws, big_ubs, big_c, big_z, clear=(0, 1.0) if fused else None)
+        bc, bz = big_c.raw(), big_z.raw()
+        for k in range(n):
+            assert np.array_equal(bc[k], sc[k % nd]), f"layer {k} colour (fused clear: {fused})"
+            assert np.array_equal(bz[k].view(np.uint32), sz[k % nd].view(np.uint32)), f"layer {k} depth (fused clear: {fused})"
+
+
 def test_row_bands_equal_full_render():
     """Multi-GPU partitioning property: rendering row bands separately gives the rows of the full render."""
     w, h = 1280, 720
