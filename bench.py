@@ -576,17 +576,35 @@ def measure(wl, args, rank, world, local_rank, steps=None, warm=None, cpu_baseli
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    trace = os.environ.get("EUC_BENCH_TRACE")  # diagnostics: host time of every call of a timed loop, collector runs
+
     def timed(fn, k, flush):
-        """k steps on the device clock: events bracket each step (so an L2 flush between steps is excluded)."""
+        """k steps on the device clock: events bracket each step (so an L2 flush between steps is excluded).  The cyclic
+        garbage collector is kept out of the loop: a collection that finds device objects of an earlier measurement frees
+        them (cudaFree / cudaFreeHost wait for the device) in the middle of the timed region."""
+        import gc
+        gc.collect()
         barrier()
+        gc.disable()
+        try:
+            return timed_inner(fn, k, flush)
+        finally:
+            gc.enable()
+
+    def timed_inner(fn, k, flush):
         if flush is None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            host = []
             a.record(stream)
             for _ in range(k):
+                t0 = time.perf_counter()
                 fn()
+                host.append(time.perf_counter() - t0)
             b.record(stream)
             barrier()
             ms = a.elapsed_time(b)
+            if trace and rank == 0:
+                print(f"[trace] {wl} k={k} device {ms:.3f} ms, host per call (ms): " + " ".join(f"{1e3 * t:.2f}" for t in host[:64]), file=sys.stderr, flush=True)
         else:
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
             for a, b in evs:
@@ -671,13 +689,19 @@ def measure(wl, args, rank, world, local_rank, steps=None, warm=None, cpu_baseli
     barrier()
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if flush_buf is None:
-        ea.record(stream)
-        run_slots(e2e_steps)
-        for _, st_o, _ in slots[1:]:
-            stream.wait_stream(st_o)
-        eb.record(stream)
-        for _, _, dr in slots:
-            dr()
+        import gc
+        gc.collect()
+        gc.disable()  # as in timed(): no collector run inside the timed region
+        try:
+            ea.record(stream)
+            run_slots(e2e_steps)
+            for _, st_o, _ in slots[1:]:
+                stream.wait_stream(st_o)
+            eb.record(stream)
+            for _, _, dr in slots:
+                dr()
+        finally:
+            gc.enable()
         barrier()
         ms_e2e = reduce_max(ea.elapsed_time(eb))
     else:
@@ -775,7 +799,7 @@ def run_ours(args, rank, world, local_rank):
             line["icon_batch"] = {"workload": ib["config"]["workload"], "icons": args.icons, "n_gpus": world, "metric": "icons_per_s", "value": ib["value"], "unit": "icons/s",
                                   "ms_per_batch": ib["ms_per_step"], "e2e": ib["e2e"], "scaling": "strong", "partition": ib["config"]["partition"],
                                   "gpu_launches": ib["gpu_launches"], "stage_ms_per_launch": ib["stage_ms_per_launch"], "fragments_per_batch": ib["fragments_per_step"],
-                                  "crc_ok": ib["frame_matches_golden_crc"], "icons_checked": ib["icons_checked"],
+                                  "host_waits_in_timed_region": ib["host_waits_in_timed_region"], "crc_ok": ib["frame_matches_golden_crc"], "icons_checked": ib["icons_checked"],
                                   "icons_depth_crc_mismatch": ib["icons_depth_crc_mismatch"], "icons_colour_crc_mismatch": ib["icons_colour_crc_mismatch"],
                                   "roofline": ib["roofline"], "steps": ib["steps"]}
     if rank == 0:

@@ -3,7 +3,7 @@
 # ncu launch list + full captures.  TAG names the outputs under gpurun_out/.
 TAG=${TAG:-r2}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_c4.json 2> gpurun_out/${TAG}_bench_c4.err
 for wl in c1 c2 c3; do
@@ -31,8 +31,13 @@ capture() {  # capture <kernel regex> <name> <bench args...>: full ncu capture, 
   ncu -i gpurun_out/${TAG}_$name.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${TAG}_${name}_source.csv 2>/dev/null
   rm -f gpurun_out/${TAG}_$name.ncu-rep
 }
-capture raster_kernel raster_c4 --no-icon-batch
-capture setup_kernel setup_c4 --no-icon-batch
-capture resolve_kernel resolve_c3 --workload c3
-capture raster_kernel raster_c5 --workload c5 --icons 1024
+CAPS=${CAPS:-"raster_c4 setup_c4 resolve_c3 raster_c5"}  # which captures to take (each costs about a minute of GPU time)
+for c in $CAPS; do
+  case $c in
+    raster_c4) capture raster_kernel raster_c4 --no-icon-batch ;;
+    setup_c4) capture setup_kernel setup_c4 --no-icon-batch ;;
+    resolve_c3) capture resolve_kernel resolve_c3 --workload c3 ;;
+    raster_c5) capture raster_kernel raster_c5 --workload c5 --icons 1024 ;;
+  esac
+done
 ls -la gpurun_out | grep ${TAG}_ | head -40
