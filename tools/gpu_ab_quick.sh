@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B of the chunked tile kernel (guided chunks): parity suite on the in-tree library, then C4 and icon batches for the in-tree
-# library, the same source without the chunked launch (build/ab/libeuc_nochunk.so) and the previous commit (libeuc_base.so)
+# parity suite on the in-tree library, then C4 / icon-batch bench lines for the in-tree library and every variant in build/ab
+# (variants: one switch of kernels.cuh flipped with -D, built with the flags of __graft_entry__.py)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -${TAIL:-25}
 run() {  # run <lib> <workload> <bench args...>
   local lib=$1 wl=$2; shift 2
   [ -f $lib ] || return
@@ -17,6 +17,6 @@ except Exception as ex:
 PY
 }
 IN=euc_b200/csrc/libeuc_b200.so
-for lib in build/ab/libeuc_base.so $IN build/ab/libeuc_nochunk.so $IN; do run $lib c4 --no-icon-batch; done
-for lib in build/ab/libeuc_nochunk.so $IN build/ab/libeuc_base.so $IN; do run $lib c5 --icons 4096 --steps 5; done
-for lib in build/ab/libeuc_nochunk.so $IN; do run $lib c5 --icons 1024 --steps 5; done
+for lib in $IN build/ab/*.so $IN; do run $lib c4 --no-icon-batch; done
+for lib in $IN build/ab/*.so $IN; do run $lib c5 --icons 4096 --steps 5; done
+for wl in ${EXTRA_WLS:-}; do for lib in $IN build/ab/*.so; do run $lib $wl; done; done
